@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the REAL reference modules
+(/root/reference, via oracle/ref_loader.py) on seeded synthetic weights and inputs.
+
+Run in the build container only:  python -m oracle.make_golden [case ...]
+The fixtures hold the reference OUTPUTS plus the checksums of the synthetic weights/inputs
+that produced them; inputs are regenerated from the seed (vista_b200/synth.py) by the tests.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+from oracle import ref_loader
+from vista_b200 import spec, synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name -> (unet preset, latent h, latent w, frames)
+UNET_CASES = {
+    "unet_tiny": ("tiny", 8, 16, 25),
+    "unet_small": ("small", 16, 32, 25),
+    "unet_vista_8x16": ("vista", 8, 16, 25),
+}
+# name -> (preset, h, w, frames, steps, guider, n cond frames)
+SAMPLER_CASES = {
+    "sampler_tiny_cfg": ("tiny", 8, 16, 25, 4, "VanillaCFG", 1),
+    "sampler_tiny_triangle": ("tiny", 8, 16, 25, 3, "TrianglePredictionGuider", 3),
+}
+# name -> (decoder preset, h, w, n latent frames)
+DECODER_CASES = {
+    "decoder_tiny": ("tiny", 8, 16, 14),
+    "decoder_small": ("small", 8, 16, 14),
+}
+DECODE_FS_CASES = {
+    "decode_first_stage_tiny": ("tiny", 8, 16, 25),
+}
+
+
+def to_t(d):
+    return {k: torch.from_numpy(v) for k, v in d.items()}
+
+
+def unet_inputs(seed, cfg, h, w, T, sigma=5.0, n_cond=1):
+    c, uc = synth.synth_conditioning(seed, T, h, w, trajectory=True, context_dim=cfg.context_dim,
+                                     adm=cfg.adm_in_channels)
+    noise, z, mask = synth.synth_latents(seed, T, h, w)
+    mask[:n_cond] = 1.0
+    x = np.concatenate([noise, noise], 0) * np.float32(sigma)
+    cc = {k: np.concatenate([uc[k], c[k]], 0) for k in c}
+    mask2 = np.concatenate([mask, mask], 0)
+    return x, cc, mask2
+
+
+def gen_unet(name):
+    preset, h, w, T = UNET_CASES[name]
+    cfg = spec.unet_preset(preset)
+    sd = synth.synth_state_dict(spec.unet_param_specs(cfg), seed=1)
+    ck = synth.state_dict_checksum(sd)
+    unet = ref_loader.build_ref_unet(cfg)
+    unet.load_state_dict(to_t(sd), strict=True)
+    ref = ref_loader.load_reference()
+    net = ref.OpenAIWrapper(unet)
+    den = ref_loader.build_ref_denoiser(T)
+    x, cc, mask2 = unet_inputs(7, cfg, h, w, T)
+    sigma = torch.full((2 * T,), 5.0)
+    t0 = time.time()
+    with torch.no_grad():
+        cct = to_t(cc)
+        out = den(net, torch.from_numpy(x), sigma, cct, torch.from_numpy(mask2))
+        # raw network output too (pre-conditioning removed)
+        c_skip, c_out, c_in, c_noise = den.scaling(sigma[:, None, None, None])
+        raw = net(torch.from_numpy(x) * c_in, c_noise.reshape(-1), cct, torch.from_numpy(mask2), T)
+    print(f"{name}: ref forward x2 {time.time() - t0:.1f}s, out absmean {out.abs().mean():.4f} raw absmean {raw.abs().mean():.4f}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), denoised=out.numpy(), raw=raw.numpy(),
+                        weight_checksum=ck, input_checksum=synth.checksum([x, mask2] + [cc[k] for k in sorted(cc)]),
+                        sigma=5.0)
+
+
+def gen_sampler(name):
+    preset, h, w, T, steps, guider, n_cond = SAMPLER_CASES[name]
+    cfg = spec.unet_preset(preset)
+    sd = synth.synth_state_dict(spec.unet_param_specs(cfg), seed=1)
+    unet = ref_loader.build_ref_unet(cfg)
+    unet.load_state_dict(to_t(sd), strict=True)
+    ref = ref_loader.load_reference()
+    net = ref.OpenAIWrapper(unet)
+    den = ref_loader.build_ref_denoiser(T)
+    smp = ref_loader.build_ref_sampler(steps, guider, 2.5, T)
+    c, uc = synth.synth_conditioning(7, T, h, w, trajectory=True, context_dim=cfg.context_dim, adm=cfg.adm_in_channels)
+    noise, z, mask = synth.synth_latents(7, T, h, w)
+    mask[:n_cond] = 1.0
+    with torch.no_grad():
+        out = smp(lambda x, s, cc, m: den(net, x, s, cc, m), torch.from_numpy(noise.copy()), cond=to_t(c), uc=to_t(uc),
+                  cond_frame=torch.from_numpy(z), cond_mask=torch.from_numpy(mask))
+    print(f"{name}: absmean {out.abs().mean():.4f}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), sample=out.numpy(),
+                        weight_checksum=synth.state_dict_checksum(sd))
+
+
+def gen_decoder(name):
+    preset, h, w, n = DECODER_CASES[name]
+    cfg = spec.decoder_preset(preset)
+    sd = synth.synth_state_dict(spec.decoder_param_specs(cfg), seed=2)
+    dec = ref_loader.build_ref_decoder(cfg)
+    dec.load_state_dict(to_t(sd), strict=True)
+    z = synth.normal(9, "dec.z", (n, cfg.z_channels, h, w), std=1.0)
+    with torch.no_grad():
+        out = dec(torch.from_numpy(z), timesteps=n)
+    print(f"{name}: out {tuple(out.shape)} absmean {out.abs().mean():.4f}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), out=out.numpy(),
+                        weight_checksum=synth.state_dict_checksum(sd))
+
+
+def gen_decode_fs(name):
+    """DiffusionEngine.decode_first_stage (models/diffusion.py:150-180) called unbound on a stand-in
+    engine object: the LightningModule itself cannot be constructed offline (conditioner needs CLIP)."""
+    preset, h, w, n = DECODE_FS_CASES[name]
+    cfg = spec.decoder_preset(preset)
+    sd = synth.synth_state_dict(spec.decoder_param_specs(cfg), seed=2)
+    dec = ref_loader.build_ref_decoder(cfg)
+    dec.load_state_dict(to_t(sd), strict=True)
+    from vwm.models.diffusion import DiffusionEngine
+    fsm = types.SimpleNamespace(decoder=dec, decode=lambda z, **kw: dec(z, **kw))
+    eng = types.SimpleNamespace(scale_factor=0.18215, en_and_decode_n_samples_a_time=14,
+                                disable_first_stage_autocast=True, first_stage_model=fsm)
+    z = synth.normal(9, "decfs.z", (n, cfg.z_channels, h, w), std=0.18215)
+    fn = DiffusionEngine.decode_first_stage
+    fn = getattr(fn, "__wrapped__", fn)
+    with torch.no_grad():
+        out = fn(eng, torch.from_numpy(z))
+    print(f"{name}: out {tuple(out.shape)} absmean {out.abs().mean():.4f}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), out=out.numpy(),
+                        weight_checksum=synth.state_dict_checksum(sd))
+
+
+def gen_anchors():
+    """Closed-form pieces straight from the reference classes."""
+    ref = ref_loader.load_reference()
+    disc = ref.discretizer.EDMDiscretization(sigma_min=0.002, sigma_max=700.0, rho=7.0)
+    out = {f"sigmas_{n}": disc(n, device="cpu").numpy() for n in (1, 3, 10, 50)}
+    sc = ref.denoiser_scaling.VScalingWithEDMcNoise()
+    s = torch.tensor([700.0, 15.59, 1.0, 0.002])
+    out["vscaling"] = torch.stack(sc(s)).numpy()
+    tri = ref.guiders.TrianglePredictionGuider(num_frames=25, max_scale=2.5, min_scale=1.0)
+    out["triangle_25"] = tri.scale.numpy()
+    lin = ref.guiders.LinearPredictionGuider(num_frames=25, max_scale=2.5, min_scale=1.0)
+    out["linear_25"] = lin.scale.numpy()
+    from vwm.modules.diffusionmodules.util import timestep_embedding
+    out["temb_320"] = timestep_embedding(torch.tensor([0.25 * np.log(700.0), -1.5, 0.0]), 320).numpy()
+    out["temb_frames_64"] = timestep_embedding(torch.arange(25), 64).numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "anchors.npz"), **out)
+    print("anchors: sigmas_3 =", out["sigmas_3"])
+
+
+def gen_full_step():
+    """BASELINE config 1: one EDM step at 25x4x72x128 with the full vista.yaml network (CPU fp32;
+    ~10 min on 8 vCPU).  Stores the step output latent (3.7 MB fp32 -> fp16-rounded copy kept too)."""
+    name = "vista_full_step"
+    cfg = spec.unet_preset("vista")
+    T, h, w = 25, 72, 128
+    sd = synth.synth_state_dict(spec.unet_param_specs(cfg), seed=1)
+    ck = synth.state_dict_checksum(sd)
+    unet = ref_loader.build_ref_unet(cfg)
+    unet.load_state_dict(to_t(sd), strict=True)
+    del sd
+    ref = ref_loader.load_reference()
+    net = ref.OpenAIWrapper(unet)
+    den = ref_loader.build_ref_denoiser(T)
+    smp = ref_loader.build_ref_sampler(1, "VanillaCFG", 2.5, T)
+    c, uc = synth.synth_conditioning(7, T, h, w, trajectory=True)
+    noise, z, mask = synth.synth_latents(7, T, h, w)
+    t0 = time.time()
+    with torch.no_grad():
+        out = smp(lambda x, s, cc, m: den(net, x, s, cc, m), torch.from_numpy(noise.copy()), cond=to_t(c), uc=to_t(uc),
+                  cond_frame=torch.from_numpy(z), cond_mask=torch.from_numpy(mask))
+    dt = time.time() - t0
+    print(f"{name}: {dt:.1f}s absmean {out.abs().mean():.4f}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), sample=out.numpy(), weight_checksum=ck,
+                        cpu_seconds=dt, cpu_threads=torch.get_num_threads())
+
+
+def main(argv):
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    cases = argv or (["anchors"] + list(UNET_CASES) + list(SAMPLER_CASES) + list(DECODER_CASES) + list(DECODE_FS_CASES))
+    for cname in cases:
+        if cname == "anchors":
+            gen_anchors()
+        elif cname in UNET_CASES:
+            gen_unet(cname)
+        elif cname in SAMPLER_CASES:
+            gen_sampler(cname)
+        elif cname in DECODER_CASES:
+            gen_decoder(cname)
+        elif cname in DECODE_FS_CASES:
+            gen_decode_fs(cname)
+        elif cname == "vista_full_step":
+            gen_full_step()
+        else:
+            raise KeyError(cname)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
