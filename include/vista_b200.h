@@ -1,0 +1,170 @@
+/*
+ * vista_b200 — C-ABI of the B200-native Vista denoising hot path.
+ *
+ * The reference (OpenDriveLab/Vista) is pure Python and has no FFI of its own; every kernel it runs
+ * is a library call reached through PyTorch.  Each entry point below replaces one family of those
+ * library call sites (reference file:line given per function, paths relative to the reference
+ * root).  The binding a reference maintainer would add is a ctypes stub — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - activations are TOKEN-MAJOR fp16: [tokens, channels] with an explicit row stride in
+ *     elements ("ld").  A (B,C,H,W) reference tensor is stored as tokens = (b*H + h)*W + w,
+ *     i.e. NHWC; the "(b t) s c" token layout of vwm/modules/video_attention.py:116 is the
+ *     same memory.  Row strides let a tensor live inside a wider buffer (skip-concat, q|k|v).
+ *   - every call is asynchronous on `stream`; the library keeps no global mutable state
+ *     besides the last-error string.  Returns 0 on success, non-zero on error
+ *     (message via b200v_last_error()).  There is NO CPU fallback.
+ */
+#ifndef VISTA_B200_H
+#define VISTA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* b200v_last_error(void);
+int b200v_version(void);
+/* Fills sm count / compute capability of the current device. */
+int b200v_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tap-GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators, fused epilogue).
+ *   out[token, n] = epilogue( sum_{tap, c} A[token shifted by tap, c] * Wt[n, tap*cin + c] )
+ * One kernel serves
+ *   nn.Linear ................ vwm/modules/attention.py:275-282,88,120,579,603 (ntaps = 1)
+ *   nn.Conv2d 3x3 pad 1 ...... vwm/modules/diffusionmodules/openaimodel.py:198,232,84; model.py:104,109,60
+ *   nn.Conv2d 1x1 ............ openaimodel.py:241; model.py:114,152-155
+ *   nn.Conv3d (3,1,1) ........ video_model.py:38-52; temporal_ae.py:25-37,83-88 (taps along frames)
+ * Epilogue (fp32):  v = s_acc*(acc + bias[n]) + rowvec[(token/rv_div)%rv_mod, n];  v = act(v);
+ *                   v += s_res1*res1[token,n] + s_res2*res2[token,n]
+ *   act: 0 none, 1 SiLU, 2 GEGLU (value*gelu_erf(gate); weights/bias pre-permuted so a tile of
+ *   tile_n columns holds tile_n/2 value columns followed by their gate columns; N counts the
+ *   permuted columns, the output has N/2 columns) — vwm/modules/attention.py:85-93.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200v_gemm_desc {
+  const void* a;        /* fp16/bf16 activations */
+  int64_t lda;          /* row stride of A in elements (multiple of 8) */
+  int64_t tokens;       /* number of A rows = NB*H*W */
+  int32_t a_mode;       /* 0: linear (2-D), 1: image taps (4-D view c,w,h,b with zero padding) */
+  int32_t W, H, NB;     /* a_mode 1: geometry of the view; a_mode 0: ignored */
+  int32_t box_w, box_h, box_b; /* a_mode 1: token tile, box_w*box_h*box_b == 128 */
+  int32_t cin;          /* channels per tap (multiple of 64) */
+  int32_t ntaps;        /* 1..9 */
+  int32_t dh[9];        /* tap offsets along h and w */
+  int32_t dw[9];
+  const void* b;        /* weights [N, ntaps*cin], K contiguous, same dtype as A */
+  int32_t N;            /* multiple of 8 */
+  int32_t tile_n;       /* 32..256, multiple of 32 */
+  int32_t bf16;         /* 0: fp16 operands, 1: bf16 operands */
+  void* out;            /* fp16 (or fp32 if out_f32) [tokens, ldo] */
+  int64_t ldo;
+  int32_t out_f32;
+  int32_t act;
+  const float* bias;    /* [N] or NULL */
+  const float* rowvec;  /* [rows, ld_rowvec] fp32 or NULL */
+  int64_t ld_rowvec;
+  int32_t rv_div, rv_mod;
+  const void* res1;     /* same dtype as out (16-bit) or NULL */
+  int64_t ld_res1;
+  float s_res1;
+  const void* res2;
+  int64_t ld_res2;
+  float s_res2;
+  float s_acc;
+} b200v_gemm_desc;
+
+int b200v_gemm(const b200v_gemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spatial self-attention, head dim 64, non-causal:  softmax(Q K^T / 8) V  per (frame, head).
+ * Replaces xformers.ops.memory_efficient_attention at vwm/modules/attention.py:401 (and the head
+ * split / merge copies at :370-378, :409-414).  q/k/v are column slices of token-major buffers:
+ * element (frame f, token t, head h, dim d) of q is q[(f*seq + t)*ld_q + h*64 + d].
+ * ---------------------------------------------------------------------------------------------- */
+int b200v_attention_spatial(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                            void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
+
+/* Temporal self-attention over the T frames of each pixel (seq len T <= 32, head dim 64).
+ * Replaces the batchified xformers call at vwm/modules/attention.py:384-399 reached from
+ * vwm/modules/video_attention.py:127 and both "(b t) s c <-> (b s) t c" rearranges (:116,:140):
+ * tokens stay in (b t) s order, the kernel strides over frames. */
+int b200v_attention_temporal(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                             void* out, int64_t ld_o, int32_t nb, int32_t T, int32_t S, int32_t heads, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (32 groups) in two phases, fp32/fp64 statistics:
+ *   stats: sums[stat, g, {sum, sumsq}] += over tokens of frames mapping to stat = frame / frames_per_stat
+ *   apply: y = (x - mean) * rstd * gamma + beta, optional SiLU, fp16 out
+ * frames_per_stat = 1 is the per-frame GroupNorm32 (vwm/modules/diffusionmodules/util.py:214-216),
+ * frames_per_stat = T is the (C/32, T, H, W) statistic of the temporal ResBlock
+ * (video_model.py:67-72 with openaimodel.py:195-199, dims=3).  `sums` must be zeroed by the caller.
+ * ---------------------------------------------------------------------------------------------- */
+int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C,
+                          int32_t groups, int32_t frames_per_stat, double* sums, void* stream);
+int b200v_groupnorm_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t frames, int32_t tokens_per_frame,
+                          int32_t C, int32_t groups, int32_t frames_per_stat, const double* sums, const float* gamma,
+                          const float* beta, float eps, int32_t silu, void* stream);
+
+/* LayerNorm over C per token (eps 1e-5), optional fp32 row-vector added to the input first:
+ *   y = LN(x + addvec[(token/av_div)%av_mod, :]).   nn.LayerNorm at attention.py:488-490,
+ * video_attention.py:49,76,97,98; the add is `x_mix = x + emb` (video_attention.py:284-285). */
+int b200v_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t tokens, int32_t C, const float* gamma,
+                    const float* beta, float eps, const float* addvec, int64_t ld_addvec, int32_t av_div,
+                    int32_t av_mod, void* stream);
+
+/* Direct convolutions for the two thin ends of the UNet / decoder (CUDA cores; < 0.1 % of FLOPs):
+ *   conv3x3_small_cin : Cin <= 8, e.g. input_blocks.0 (video_model.py:189), decoder conv_in (model.py:604)
+ *   conv3x3_small_cout: Cout <= 4, e.g. out[2] (video_model.py:438), AE3DConv's Conv2d (temporal_ae.py:91) */
+int b200v_conv3x3_small_cin(const void* x, int32_t cin, const float* w /* [cout,cin,3,3] */, const float* bias,
+                            void* out, int64_t ldo, int32_t NB, int32_t H, int32_t W, int32_t cout, void* stream);
+int b200v_conv3x3_small_cout(const void* x, int64_t ldx, int32_t cin, const float* w /* [cout,cin,3,3] */,
+                             const float* bias, float* out /* [tokens, cout] fp32 */, int32_t NB, int32_t H, int32_t W,
+                             int32_t cout, void* stream);
+
+/* Data movement: stride-2 im2col for Downsample (openaimodel.py:129-136), nearest 2x upsample
+ * (openaimodel.py:100; model.py:63). */
+int b200v_im2col_s2(const void* x, int64_t ldx, void* out, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream);
+int b200v_upsample2x(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t NB, int32_t H, int32_t W, int32_t C,
+                     void* stream);
+
+/* Small fp32 helpers of the embedding path:
+ *   timestep_embedding: out[i, :] = cos||sin(t[i] * freqs)   (util.py:141-165), fp16 out
+ *   silu_f16: y = silu(x) fp32 -> fp16 (emb_layers' nn.SiLU, openaimodel.py:222-225)
+ *   blend_emb: emb = e_cond*m + e_plain*(1-m) + label   (video_model.py:457-471) */
+int b200v_timestep_embedding(const float* t, int32_t n, int32_t dim, float max_period, void* out_f16, int64_t ldo,
+                             void* stream);
+int b200v_blend_emb(const float* e_plain, const float* e_cond, const float* label, const float* mask, float* emb_f32,
+                    void* silu_emb_f16, int32_t rows, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused EDM / Euler sampler step around the UNet call (all fp32 state, NCHW latents (T,4,h,w)):
+ *   prepare: x = x*(1-mask) + cond_frame*mask                       (sampling.py:105-106)
+ *            unet_in[(2T),h,w,8] = [x*c_in(sigma) | concat]  fp16   (guiders.py:28-36, denoiser.py:33-35,
+ *                                                                     wrappers.py:31), rows [uncond; cond]
+ *            c_noise[2T] = 0.25*ln(sigma)                           (denoiser_scaling.py:58)
+ *   update : D_u/c = net*c_out + x*c_skip; D = D_u + scale[t]*(D_c - D_u)   (guiders.py:23-26,68-74)
+ *            x += (x - D)/sigma * (sigma_next - sigma)              (sampling_utils.py:46, sampling.py:85-88)
+ *            and, when `final`, re-imposes the conditioning frames  (sampling.py:122-123)
+ * sigma values are read from the device array `sigmas` at index *step_idx (device int); update
+ * increments *step_idx so that a captured CUDA graph can be replayed for every step.
+ * ---------------------------------------------------------------------------------------------- */
+int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask, const float* concat_c /* (T,4,h,w) or NULL */,
+                          const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
+                          int32_t T, int32_t h, int32_t w, void* stream);
+int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, 4] fp32 token-major */, const float* cond_frame,
+                         const float* mask, const float* scales /* [T] */, const float* sigmas, int32_t* step_idx,
+                         int32_t num_steps, int32_t T, int32_t h, int32_t w, void* stream);
+
+/* Layout converters at the boundary: NCHW fp32 <-> token-major (NHWC) fp16/fp32. */
+int b200v_nchw_to_tokens(const float* x, void* out_f16, int64_t ldo, int32_t NB, int32_t C, int32_t H, int32_t W,
+                         void* stream);
+int b200v_tokens_to_nchw(const void* x, int32_t x_is_f32, int64_t ldx, float* out, int32_t NB, int32_t C, int32_t H,
+                         int32_t W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISTA_B200_H */

@@ -1,0 +1,717 @@
+// HBM-bound kernels of the path: GroupNorm (stats / apply+SiLU), LayerNorm, temporal attention
+// (sequence = frames of one pixel), thin direct convolutions, data movement, embedding helpers,
+// the fused EDM/Euler sampler step and the layout converters.  All activations are token-major
+// fp16 with explicit row strides; every kernel uses 16-byte vector accesses along channels.
+#include "../../include/vista_b200.h"
+#include "host.cuh"
+#include "ptx.cuh"
+
+namespace vb {
+
+__device__ __forceinline__ void h8_to_f(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f_to_h8(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics.  grid = (chunks, frames); a block walks `chunk` tokens of one frame; thread
+// (row, lane) owns the 8-channel vectors lane, lane+L, ... and keeps per-channel fp32 partials that
+// are reduced per group in shared memory and added to the fp64 global sums.
+// ------------------------------------------------------------------------------------------
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxJ = 4;  // vectors per thread (C <= 8 * L * kGnMaxJ)
+
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_frame, int C, int groups,
+                int frames_per_stat, int chunk, int L, int J, double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2*C]
+  const int frame = blockIdx.y;
+  const int t0 = blockIdx.x * chunk;
+  const int t1 = min(t0 + chunk, tokens_per_frame);
+  const int nvec = C >> 3;
+  const int rows = kGnThreads / L;
+  const int lane = threadIdx.x % L, row = threadIdx.x / L;
+  for (int i = threadIdx.x; i < 2 * C; i += kGnThreads) sh[i] = 0.f;
+  __syncthreads();
+  float s[kGnMaxJ][8], q[kGnMaxJ][8];
+#pragma unroll
+  for (int j = 0; j < kGnMaxJ; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[j][i] = q[j][i] = 0.f;
+  if (row < rows) {
+    const __half* base = x + ((long long)frame * tokens_per_frame) * ldx;
+    for (int t = t0 + row; t < t1; t += rows) {
+#pragma unroll
+      for (int j = 0; j < kGnMaxJ; ++j) {
+        const int v = lane + j * L;
+        if (j < J && v < nvec) {
+          float f[8];
+          h8_to_f(__ldg(reinterpret_cast<const uint4*>(base + (long long)t * ldx + v * 8)), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s[j][i] += f[i];
+            q[j][i] += f[i] * f[i];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kGnMaxJ; ++j) {
+      const int v = lane + j * L;
+      if (j < J && v < nvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          atomicAdd(&sh[v * 8 + i], s[j][i]);
+          atomicAdd(&sh[C + v * 8 + i], q[j][i]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+    double a = 0.0, b = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += (double)sh[c];
+      b += (double)sh[C + c];
+    }
+    double* dst = sums + ((long long)(frame / frames_per_stat) * groups + g) * 2;
+    atomicAdd(dst, a);
+    atomicAdd(dst + 1, b);
+  }
+}
+
+// apply: grid = (chunks, frames); y = (x-mean)*rstd*gamma + beta, optional SiLU
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
+                int tokens_per_frame, int C, int groups, int frames_per_stat, int chunk,
+                const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int silu) {
+  extern __shared__ float sh[];  // scale[C], shift[C]
+  const int frame = blockIdx.y;
+  const int cpg = C / groups;
+  const double cnt = (double)cpg * tokens_per_frame * frames_per_stat;
+  const double* st = sums + (long long)(frame / frames_per_stat) * groups * 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = st[2 * g] / cnt;
+    double var = st[2 * g + 1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = rstd * gamma[c];
+    sh[c] = sc;
+    sh[C + c] = beta[c] - (float)mean * sc;
+  }
+  __syncthreads();
+  const int nvec = C >> 3;
+  const int t0 = blockIdx.x * chunk;
+  const int n = min(chunk, tokens_per_frame - t0);
+  const long long tok0 = (long long)frame * tokens_per_frame + t0;
+  for (int idx = threadIdx.x; idx < n * nvec; idx += blockDim.x) {
+    const int t = idx / nvec, v = idx - t * nvec;
+    float f[8];
+    h8_to_f(__ldg(reinterpret_cast<const uint4*>(x + (tok0 + t) * ldx + v * 8)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float r = f[i] * sh[v * 8 + i] + sh[C + v * 8 + i];
+      f[i] = silu ? silu_f(r) : r;
+    }
+    *reinterpret_cast<uint4*>(y + (tok0 + t) * ldy + v * 8) = f_to_h8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per token, values kept in registers (C <= 2560), two-pass statistics.
+// ------------------------------------------------------------------------------------------
+constexpr int kLnMaxV = 10;  // vectors of 8 per lane
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, long long tokens,
+                 int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 const float* __restrict__ addvec, long long ld_addvec, int av_div, int av_mod) {
+  const int lane = threadIdx.x & 31;
+  const long long token = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (token >= tokens) return;
+  const int nvec = C >> 3;
+  float v[kLnMaxV][8];
+  const float* av = addvec ? addvec + ((token / av_div) % av_mod) * ld_addvec : nullptr;
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      h8_to_f(__ldg(reinterpret_cast<const uint4*>(x + token * ldx + vi * 8)), v[j]);
+      if (av) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j][i] += __ldg(av + vi * 8 + i);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[j][i];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[j][i] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+  for (int j = 0; j < kLnMaxV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * __ldg(gamma + vi * 8 + i) + __ldg(beta + vi * 8 + i);
+      *reinterpret_cast<uint4*>(y + token * ldy + vi * 8) = f_to_h8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Temporal attention: one block per (clip, pixel, group of 4 heads), one warp per head.  K and V of the T frames
+// (T <= 32, d = 64) sit in shared memory; lane t owns query frame t.  Bandwidth bound.
+// ------------------------------------------------------------------------------------------
+__global__ void attn_temporal_kernel(const __half* __restrict__ q, long long ld_q, const __half* __restrict__ k,
+                                     long long ld_k, const __half* __restrict__ v, long long ld_v,
+                                     __half* __restrict__ out, long long ld_o, int T, int S, int heads) {
+  extern __shared__ __half shkv[];  // per warp: K[T][64], V[T][64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int head = blockIdx.z * 4 + warp;
+  if (head >= heads) return;
+  __half* sK = shkv + (size_t)warp * 2 * T * 64;
+  __half* sV = sK + T * 64;
+  const long long tok0 = (long long)b * T * S + s;  // token of frame 0; frame t adds t*S
+  // cooperative load: T rows x 8 vectors (16 B) for K and V
+  for (int i = lane; i < T * 8; i += 32) {
+    const int t = i >> 3, c = i & 7;
+    const long long tok = tok0 + (long long)t * S;
+    reinterpret_cast<uint4*>(sK)[i] = __ldg(reinterpret_cast<const uint4*>(k + tok * ld_k + head * 64 + c * 8));
+    reinterpret_cast<uint4*>(sV)[i] = __ldg(reinterpret_cast<const uint4*>(v + tok * ld_v + head * 64 + c * 8));
+  }
+  __syncwarp();
+  if (lane < T) {
+    const long long tok = tok0 + (long long)lane * S;
+    float qf[64];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float f[8];
+      h8_to_f(__ldg(reinterpret_cast<const uint4*>(q + tok * ld_q + head * 64 + c * 8)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qf[c * 8 + i] = f[i] * 0.125f;  // 64^-0.5
+    }
+    float sc[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      sc[j] = -INFINITY;
+      if (j < T) {
+        float a = 0.f;
+        const __half2* kr = reinterpret_cast<const __half2*>(sK + j * 64);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          const float2 kk = __half22float2(kr[d]);
+          a = fmaf(qf[2 * d], kk.x, a);
+          a = fmaf(qf[2 * d + 1], kk.y, a);
+        }
+        sc[j] = a;
+        mx = fmaxf(mx, a);
+      }
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < T) {
+        sc[j] = __expf(sc[j] - mx);
+        l += sc[j];
+      }
+    }
+    const float inv = 1.0f / l;
+    float o[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < T) {
+        const float pj = sc[j] * inv;
+        const __half2* vr = reinterpret_cast<const __half2*>(sV + j * 64);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          const float2 vv = __half22float2(vr[d]);
+          o[2 * d] = fmaf(pj, vv.x, o[2 * d]);
+          o[2 * d + 1] = fmaf(pj, vv.y, o[2 * d + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = o[c * 8 + i];
+      *reinterpret_cast<uint4*>(out + tok * ld_o + head * 64 + c * 8) = f_to_h8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Thin direct convolutions
+// ------------------------------------------------------------------------------------------
+// Cin <= 8 : x is token-major fp16 [tokens, 8] (channels >= cin are ignored), out [tokens, ldo] fp16.
+// block = 256 threads handles 32 tokens; thread n loops over output channels.
+__global__ void __launch_bounds__(256)
+conv3x3_small_cin_kernel(const __half* __restrict__ x, int cin, const float* __restrict__ w,
+                         const float* __restrict__ bias, __half* __restrict__ out, long long ldo, int NB, int H, int W,
+                         int cout) {
+  __shared__ float patch[32][72];
+  const long long tok0 = (long long)blockIdx.x * 32;
+  const long long tokens = (long long)NB * H * W;
+  for (int i = threadIdx.x; i < 32 * 9; i += blockDim.x) {
+    const int t = i / 9, tap = i - t * 9;
+    const long long tok = tok0 + t;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (tok < tokens) {
+      const int wq = (int)(tok % W), hq = (int)((tok / W) % H);
+      const long long b = tok / ((long long)W * H);
+      const int hh = hq + tap / 3 - 1, ww = wq + tap % 3 - 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+        h8_to_f(__ldg(reinterpret_cast<const uint4*>(x + ((b * H + hh) * W + ww) * 8)), f);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) patch[t][tap * 8 + c] = f[c];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < cout; n += blockDim.x) {
+    float wr[72];
+#pragma unroll
+    for (int i = 0; i < 72; ++i) wr[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+        if (c < cin) wr[tap * 8 + c] = __ldg(w + ((long long)n * cin + c) * 9 + tap);
+    const float bv = bias ? __ldg(bias + n) : 0.f;
+    for (int t = 0; t < 32; ++t) {
+      const long long tok = tok0 + t;
+      if (tok >= tokens) break;
+      float a = bv;
+#pragma unroll
+      for (int i = 0; i < 72; ++i) a = fmaf(patch[t][i], wr[i], a);
+      out[tok * ldo + n] = __float2half_rn(a);
+    }
+  }
+}
+
+// Cout <= 4: one warp per token; weights [cout][9][cin] fp32 staged in shared memory as fp16.
+__global__ void __launch_bounds__(256)
+conv3x3_small_cout_kernel(const __half* __restrict__ x, long long ldx, int cin, const float* __restrict__ w,
+                          const float* __restrict__ bias, float* __restrict__ out, int NB, int H, int W, int cout) {
+  extern __shared__ __half shw[];  // [cout][9][cin]
+  for (int i = threadIdx.x; i < cout * 9 * cin; i += blockDim.x) {
+    const int o = i / (9 * cin), r = i - o * 9 * cin;
+    const int tap = r / cin, c = r - tap * cin;
+    shw[i] = __float2half_rn(__ldg(w + ((long long)o * cin + c) * 9 + tap));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long tokens = (long long)NB * H * W;
+  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= tokens) return;
+  const int wq = (int)(tok % W), hq = (int)((tok / W) % H);
+  const long long b = tok / ((long long)W * H);
+  const int nvec = cin >> 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = hq + tap / 3 - 1, ww = wq + tap % 3 - 1;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const __half* xp = x + ((b * H + hh) * W + ww) * ldx;
+    for (int v = lane; v < nvec; v += 32) {
+      float f[8];
+      h8_to_f(__ldg(reinterpret_cast<const uint4*>(xp + v * 8)), f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (o < cout) {
+          float g[8];
+          h8_to_f(*reinterpret_cast<const uint4*>(shw + ((long long)o * 9 + tap) * cin + v * 8), g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[o] = fmaf(f[i], g[i], acc[o]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
+  if (lane == 0) {
+    for (int o = 0; o < cout; ++o) out[tok * cout + o] = acc[o] + (bias ? __ldg(bias + o) : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Data movement
+// ------------------------------------------------------------------------------------------
+// out[(b, ho, wo), tap*C + c] = x[b, 2ho + kh - 1, 2wo + kw - 1, c] (zero padded), Ho = (H+1)/2
+__global__ void im2col_s2_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ out, int NB, int H,
+                                 int W, int C) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int nvec = C >> 3;
+  const long long total = (long long)NB * Ho * Wo * 9 * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long r = i / nvec;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho);
+    const long long b = r / ((long long)Wo * Ho);
+    const int hh = 2 * ho + tap / 3 - 1, ww = 2 * wo + tap % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      val = __ldg(reinterpret_cast<const uint4*>(x + ((b * H + hh) * W + ww) * ldx + v * 8));
+    *reinterpret_cast<uint4*>(out + r * (9LL * C) + (long long)tap * C + v * 8) = val;
+  }
+}
+
+__global__ void upsample2x_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ out, long long ldo,
+                                  int NB, int H, int W, int C) {
+  const int nvec = C >> 3;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)NB * Ho * Wo * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const long long r = i / nvec;
+    const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho);
+    const long long b = r / ((long long)Wo * Ho);
+    *reinterpret_cast<uint4*>(out + r * ldo + v * 8) =
+        __ldg(reinterpret_cast<const uint4*>(x + ((b * H + (ho >> 1)) * W + (wo >> 1)) * ldx + v * 8));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Embedding helpers
+// ------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, float max_period,
+                                          __half* __restrict__ out, long long ldo) {
+  const int half_dim = dim >> 1;
+  const int i = blockIdx.x;
+  for (int k = threadIdx.x; k < half_dim; k += blockDim.x) {
+    const float freq = expf(-logf(max_period) * (float)k / (float)half_dim);
+    const float a = t[i] * freq;
+    out[i * ldo + k] = __float2half_rn(cosf(a));
+    out[i * ldo + half_dim + k] = __float2half_rn(sinf(a));
+  }
+}
+
+__global__ void blend_emb_kernel(const float* __restrict__ e_plain, const float* __restrict__ e_cond,
+                                 const float* __restrict__ label, const float* __restrict__ mask,
+                                 float* __restrict__ emb, __half* __restrict__ silu_emb, int rows, int dim) {
+  const long long total = (long long)rows * dim;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / dim);
+    const float m = mask ? mask[r] : 0.f;
+    float e = e_plain[i] * (1.f - m);
+    if (e_cond) e += e_cond[i] * m;
+    if (label) e += label[i];
+    if (emb) emb[i] = e;
+    if (silu_emb) silu_emb[i] = __float2half_rn(silu_f(e));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Sampler step (fp32 state)
+// ------------------------------------------------------------------------------------------
+// one thread per latent pixel (t, y, x); handles the 4 channels
+__global__ void sampler_prepare_kernel(float* __restrict__ x, const float* __restrict__ cond_frame,
+                                       const float* __restrict__ mask, const float* __restrict__ concat_c,
+                                       const float* __restrict__ sigmas, const int* __restrict__ step_idx,
+                                       __half* __restrict__ unet_in, float* __restrict__ c_noise, int T, int h, int w) {
+  const float sigma = sigmas[*step_idx];
+  const float c_in = rsqrtf(sigma * sigma + 1.0f);
+  const int hw = h * w;
+  const long long total = (long long)T * hw;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * T && c_noise) c_noise[i] = 0.25f * logf(sigma);
+  if (i >= total) return;
+  const int t = (int)(i / hw), pix = (int)(i % hw);
+  const float m = mask ? mask[t] : 0.f;
+  float xv[8], cu[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const long long idx = ((long long)t * 4 + c) * hw + pix;
+    float v = x[idx];
+    if (mask && cond_frame) {
+      v = v * (1.f - m) + cond_frame[idx] * m;
+      x[idx] = v;
+    }
+    xv[c] = v * c_in;
+    cu[c] = xv[c];
+    xv[4 + c] = 0.f;                                   // uncond rows: concat zeroed (sample.py:243)
+    cu[4 + c] = concat_c ? concat_c[idx] : 0.f;        // cond rows
+  }
+  *reinterpret_cast<uint4*>(unet_in + ((long long)t * hw + pix) * 8) = f_to_h8(xv);
+  *reinterpret_cast<uint4*>(unet_in + (((long long)T + t) * hw + pix) * 8) = f_to_h8(cu);
+}
+
+__global__ void sampler_update_kernel(float* __restrict__ x, const float* __restrict__ net,
+                                      const float* __restrict__ cond_frame, const float* __restrict__ mask,
+                                      const float* __restrict__ scales, const float* __restrict__ sigmas,
+                                      const int* __restrict__ step_idx, int num_steps, int T, int h, int w) {
+  const int step = *step_idx;
+  const float sigma = sigmas[step], sigma_next = sigmas[step + 1];
+  const float c_skip = 1.0f / (sigma * sigma + 1.0f);
+  const float c_out = -sigma * rsqrtf(sigma * sigma + 1.0f);
+  const int hw = h * w;
+  const long long total = (long long)T * hw;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int t = (int)(i / hw), pix = (int)(i % hw);
+  const float4 nu = *reinterpret_cast<const float4*>(net + ((long long)t * hw + pix) * 4);
+  const float4 nc = *reinterpret_cast<const float4*>(net + (((long long)T + t) * hw + pix) * 4);
+  const float un[4] = {nu.x, nu.y, nu.z, nu.w}, cn[4] = {nc.x, nc.y, nc.z, nc.w};
+  const float sc = scales[t];
+  const bool final_step = (step + 1 == num_steps);
+  const float m = mask ? mask[t] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const long long idx = ((long long)t * 4 + c) * hw + pix;
+    const float xv = x[idx];
+    const float du = un[c] * c_out + xv * c_skip;
+    const float dc = cn[c] * c_out + xv * c_skip;
+    const float den = du + sc * (dc - du);
+    const float d = (xv - den) / sigma;
+    float xn = xv + d * (sigma_next - sigma);
+    if (final_step && mask && cond_frame) xn = xn * (1.f - m) + cond_frame[idx] * m;
+    x[idx] = xn;
+  }
+}
+__global__ void step_inc_kernel(int* step_idx) { *step_idx += 1; }
+
+// ------------------------------------------------------------------------------------------
+// Layout converters
+// ------------------------------------------------------------------------------------------
+__global__ void nchw_to_tokens_kernel(const float* __restrict__ x, __half* __restrict__ out, long long ldo, int NB,
+                                      int C, int H, int W) {
+  const long long total = (long long)NB * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long tok = i / C;
+    const int pix = (int)(tok % ((long long)H * W));
+    const long long b = tok / ((long long)H * W);
+    out[tok * ldo + c] = __float2half_rn(x[(b * C + c) * (long long)H * W + pix]);
+  }
+}
+__global__ void tokens_to_nchw_kernel(const void* __restrict__ x, int is_f32, long long ldx, float* __restrict__ out,
+                                      int NB, int C, int H, int W) {
+  const long long total = (long long)NB * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % ((long long)H * W));
+    const long long bc = i / ((long long)H * W);
+    const int c = (int)(bc % C);
+    const long long b = bc / C;
+    const long long tok = b * H * W + pix;
+    out[i] = is_f32 ? reinterpret_cast<const float*>(x)[tok * ldx + c]
+                    : __half2float(reinterpret_cast<const __half*>(x)[tok * ldx + c]);
+  }
+}
+
+static inline int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C,
+                                     int32_t groups, int32_t frames_per_stat, double* sums, void* stream) {
+  VB_REQUIRE(x && sums, "groupnorm_stats: null pointer");
+  VB_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0, "groupnorm_stats: C=%d groups=%d ldx=%lld invalid", C, groups,
+             (long long)ldx);
+  VB_REQUIRE(frames_per_stat > 0 && frames % frames_per_stat == 0, "groupnorm_stats: frames %% frames_per_stat != 0");
+  const int nvec = C / 8;
+  int L = nvec, J = 1;
+  while (L > kGnThreads) {  // split vectors over J passes
+    ++J;
+    L = (nvec + J - 1) / J;
+  }
+  VB_REQUIRE(J <= kGnMaxJ, "groupnorm_stats: C=%d too large", C);
+  const int chunk = 256;
+  dim3 grid((tokens_per_frame + chunk - 1) / chunk, frames);
+  gn_stats_kernel<<<grid, kGnThreads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, tokens_per_frame, C, groups, frames_per_stat, chunk, L, J, sums);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_groupnorm_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t frames,
+                                     int32_t tokens_per_frame, int32_t C, int32_t groups, int32_t frames_per_stat,
+                                     const double* sums, const float* gamma, const float* beta, float eps,
+                                     int32_t silu, void* stream) {
+  VB_REQUIRE(x && y && sums && gamma && beta, "groupnorm_apply: null pointer");
+  VB_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_apply: bad C/ld");
+  VB_REQUIRE(frames_per_stat > 0 && frames % frames_per_stat == 0, "groupnorm_apply: frames %% frames_per_stat != 0");
+  const int chunk = 64;
+  dim3 grid((tokens_per_frame + chunk - 1) / chunk, frames);
+  gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, (__half*)y, ldy, tokens_per_frame, C, groups, frames_per_stat, chunk, sums, gamma, beta,
+      eps, silu);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t tokens, int32_t C,
+                               const float* gamma, const float* beta, float eps, const float* addvec,
+                               int64_t ld_addvec, int32_t av_div, int32_t av_mod, void* stream) {
+  VB_REQUIRE(x && y && gamma && beta, "layernorm: null pointer");
+  VB_REQUIRE(C % 8 == 0 && C <= kLnMaxV * 256 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm: C=%d unsupported", C);
+  VB_REQUIRE(!addvec || (av_div > 0 && av_mod > 0), "layernorm: bad addvec args");
+  const int wpb = 8;
+  layernorm_kernel<<<(unsigned)((tokens + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, (__half*)y, ldy, tokens, C, gamma, beta, eps, addvec, ld_addvec, av_div > 0 ? av_div : 1,
+      av_mod > 0 ? av_mod : 1);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_attention_temporal(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
+                                        int64_t ld_v, void* out, int64_t ld_o, int32_t nb, int32_t T, int32_t S,
+                                        int32_t heads, void* stream) {
+  VB_REQUIRE(q && k && v && out, "attention_temporal: null pointer");
+  VB_REQUIRE(T >= 1 && T <= 32 && heads >= 1, "attention_temporal: T=%d heads=%d unsupported", T, heads);
+  VB_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 8 == 0, "attention_temporal: bad ld");
+  const size_t smem = (size_t)4 * 2 * T * 64 * sizeof(__half);
+  dim3 grid(S, nb, (heads + 3) / 4);
+  attn_temporal_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const __half*)q, ld_q, (const __half*)k, ld_k,
+                                                                         (const __half*)v, ld_v, (__half*)out, ld_o, T,
+                                                                         S, heads);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_conv3x3_small_cin(const void* x, int32_t cin, const float* w, const float* bias, void* out,
+                                       int64_t ldo, int32_t NB, int32_t H, int32_t W, int32_t cout, void* stream) {
+  VB_REQUIRE(x && w && out, "conv3x3_small_cin: null pointer");
+  VB_REQUIRE(cin >= 1 && cin <= 8, "conv3x3_small_cin: cin=%d > 8", cin);
+  const long long tokens = (long long)NB * H * W;
+  conv3x3_small_cin_kernel<<<(unsigned)((tokens + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, cin, w, bias, (__half*)out, ldo, NB, H, W, cout);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_conv3x3_small_cout(const void* x, int64_t ldx, int32_t cin, const float* w, const float* bias,
+                                        float* out, int32_t NB, int32_t H, int32_t W, int32_t cout, void* stream) {
+  VB_REQUIRE(x && w && out, "conv3x3_small_cout: null pointer");
+  VB_REQUIRE(cout >= 1 && cout <= 4 && cin % 8 == 0 && ldx % 8 == 0, "conv3x3_small_cout: cout=%d cin=%d unsupported",
+             cout, cin);
+  const long long tokens = (long long)NB * H * W;
+  const size_t smem = (size_t)cout * 9 * cin * sizeof(__half);
+  conv3x3_small_cout_kernel<<<(unsigned)((tokens + 7) / 8), 256, smem, (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, cin, w, bias, out, NB, H, W, cout);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_im2col_s2(const void* x, int64_t ldx, void* out, int32_t NB, int32_t H, int32_t W, int32_t C,
+                               void* stream) {
+  VB_REQUIRE(x && out && C % 8 == 0 && ldx % 8 == 0, "im2col_s2: bad args");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)NB * Ho * Wo * 9 * (C / 8);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)out, NB, H,
+                                                                           W, C);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_upsample2x(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t NB, int32_t H, int32_t W,
+                                int32_t C, void* stream) {
+  VB_REQUIRE(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "upsample2x: bad args");
+  const long long total = (long long)NB * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)out, ldo,
+                                                                            NB, H, W, C);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_timestep_embedding(const float* t, int32_t n, int32_t dim, float max_period, void* out_f16,
+                                        int64_t ldo, void* stream) {
+  VB_REQUIRE(t && out_f16 && dim % 2 == 0, "timestep_embedding: bad args");
+  timestep_embedding_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(t, n, dim, max_period, (__half*)out_f16, ldo);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_blend_emb(const float* e_plain, const float* e_cond, const float* label, const float* mask,
+                               float* emb_f32, void* silu_emb_f16, int32_t rows, int32_t dim, void* stream) {
+  VB_REQUIRE(e_plain, "blend_emb: null pointer");
+  blend_emb_kernel<<<grid_for((long long)rows * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+      e_plain, e_cond, label, mask, emb_f32, (__half*)silu_emb_f16, rows, dim);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask, const float* concat_c,
+                                     const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
+                                     int32_t T, int32_t h, int32_t w, void* stream) {
+  VB_REQUIRE(x && sigmas && step_idx && unet_in_f16, "sampler_prepare: null pointer");
+  const long long total = (long long)T * h * w;
+  sampler_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, cond_frame, mask, concat_c, sigmas, step_idx, (__half*)unet_in_f16, c_noise, T, h, w);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_sampler_update(float* x, const float* net_out, const float* cond_frame, const float* mask,
+                                    const float* scales, const float* sigmas, int32_t* step_idx, int32_t num_steps,
+                                    int32_t T, int32_t h, int32_t w, void* stream) {
+  VB_REQUIRE(x && net_out && scales && sigmas && step_idx, "sampler_update: null pointer");
+  const long long total = (long long)T * h * w;
+  sampler_update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_steps, T, h, w);
+  step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_idx);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_nchw_to_tokens(const float* x, void* out_f16, int64_t ldo, int32_t NB, int32_t C, int32_t H,
+                                    int32_t W, void* stream) {
+  VB_REQUIRE(x && out_f16, "nchw_to_tokens: null pointer");
+  nchw_to_tokens_kernel<<<grid_for((long long)NB * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (__half*)out_f16, ldo, NB, C, H, W);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_tokens_to_nchw(const void* x, int32_t x_is_f32, int64_t ldx, float* out, int32_t NB, int32_t C,
+                                    int32_t H, int32_t W, void* stream) {
+  VB_REQUIRE(x && out, "tokens_to_nchw: null pointer");
+  tokens_to_nchw_kernel<<<grid_for((long long)NB * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x, x_is_f32, ldx,
+                                                                                                    out, NB, C, H, W);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

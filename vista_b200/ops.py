@@ -1,0 +1,204 @@
+"""Python-side call wrappers over the C-ABI (include/vista_b200.h).
+
+torch is used only for device memory and streams: every function takes CUDA tensors, hands their
+raw pointers and the current stream to the library, and returns the (pre-allocated) output.
+Activations are token-major fp16 ``[tokens, C]`` views (row stride = ``tensor.stride(0)``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as _lib
+
+TAPS_3X3 = [(dh, dw) for dh in (-1, 0, 1) for dw in (-1, 0, 1)]   # tap index = kh*3 + kw
+TAPS_T3 = [(-1, 0), (0, 0), (1, 0)]                              # (3,1,1) conv: taps along frames
+TAPS_1 = [(0, 0)]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: torch.Tensor) -> Tuple[int, int]:
+    assert t.dim() == 2 and t.stride(1) == 1, "token-major 2-D view with unit channel stride expected"
+    return t.shape[0], t.stride(0)
+
+
+def pick_box(W: int, H: int, NB: int) -> Tuple[int, int, int]:
+    """Token tile (box_w, box_h, box_b) with product 128 minimising padded work."""
+    best, best_cost = None, None
+    for bw in (128, 64, 32, 16, 8, 4, 2, 1):
+        for bh in (1, 2, 4, 8, 16, 32, 64, 128):
+            if bw * bh > 128:
+                continue
+            bb = 128 // (bw * bh)
+            tiles = -(-W // bw) * -(-H // bh) * -(-NB // bb)
+            cost = (tiles, -bw)
+            if best_cost is None or cost < best_cost:
+                best, best_cost = (bw, bh, bb), cost
+    return best
+
+
+def pick_tile_n(N: int, geglu: bool = False) -> int:
+    """Largest tile_n <= 256 (multiple of 32, of 64 for GEGLU) that wastes the least of N."""
+    step = 64 if geglu else 32
+    best, best_cost = None, None
+    for tn in range(256, step - 1, -step):
+        if geglu and N % tn:
+            continue
+        tiles = -(-N // tn)
+        cost = (tiles * tn - N, tiles)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = tn, cost
+    if best is None:
+        raise ValueError(f"no tile_n for N={N} geglu={geglu}")
+    return best
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[Tuple[int, int]] = TAPS_1,
+         geom: Optional[Tuple[int, int, int]] = None, bias: Optional[torch.Tensor] = None,
+         rowvec: Optional[torch.Tensor] = None, rv_div: int = 1, rv_mod: int = 1,
+         res1: Optional[torch.Tensor] = None, s_res1: float = 1.0,
+         res2: Optional[torch.Tensor] = None, s_res2: float = 1.0,
+         s_acc: float = 1.0, act: int = 0, tile_n: Optional[int] = None, cin: Optional[int] = None) -> torch.Tensor:
+    """out = epilogue(tap-GEMM(a, w)).  ``a``: [tokens, >=cin] fp16 view; ``w``: [N, ntaps*cin] fp16;
+    ``geom`` = (W, H, NB) turns on image taps (zero padded); act 2 = GEGLU (out has N/2 columns)."""
+    tokens, lda = _rows(a)
+    N, K = w.shape
+    ntaps = len(taps)
+    cin = cin if cin is not None else K // ntaps
+    assert K == ntaps * cin and w.is_contiguous()
+    d = _lib.GemmDesc()
+    d.a, d.lda, d.tokens = a.data_ptr(), lda, tokens
+    if geom is None:
+        assert ntaps == 1
+        d.a_mode = 0
+    else:
+        d.a_mode = 1
+        d.W, d.H, d.NB = geom
+        assert geom[0] * geom[1] * geom[2] == tokens
+        d.box_w, d.box_h, d.box_b = pick_box(*geom)
+    d.cin, d.ntaps = cin, ntaps
+    for i, (dh, dw) in enumerate(taps):
+        d.dh[i], d.dw[i] = dh, dw
+    d.b, d.N = w.data_ptr(), N
+    d.tile_n = tile_n if tile_n is not None else pick_tile_n(N, act == 2)
+    d.bf16 = 1 if a.dtype == torch.bfloat16 else 0
+    _, ldo = _rows(out)
+    d.out, d.ldo, d.out_f32, d.act = out.data_ptr(), ldo, int(out.dtype == torch.float32), act
+    d.bias = _ptr(bias)
+    if rowvec is not None:
+        d.rowvec, d.ld_rowvec, d.rv_div, d.rv_mod = rowvec.data_ptr(), rowvec.stride(0), rv_div, rv_mod
+    if res1 is not None:
+        d.res1, d.ld_res1, d.s_res1 = res1.data_ptr(), res1.stride(0), s_res1
+    if res2 is not None:
+        d.res2, d.ld_res2, d.s_res2 = res2.data_ptr(), res2.stride(0), s_res2
+    d.s_acc = s_acc
+    _lib.check(_lib.load().b200v_gemm(C.byref(d), _stream()), "b200v_gemm")
+    return out
+
+
+def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int):
+    _lib.check(_lib.load().b200v_attention_spatial(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+                                                   v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
+                                                   frames, seq, heads, _stream()), "b200v_attention_spatial")
+    return out
+
+
+def attention_temporal(q, k, v, out, nb: int, T: int, S: int, heads: int):
+    _lib.check(_lib.load().b200v_attention_temporal(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+                                                    v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
+                                                    nb, T, S, heads, _stream()), "b200v_attention_temporal")
+    return out
+
+
+def groupnorm(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float, silu: bool,
+              sums: torch.Tensor, frames_per_stat: int = 1, groups: int = 32):
+    """Two-phase GroupNorm; ``sums`` ([frames/frames_per_stat, groups, 2] fp64) must be zero on entry."""
+    Cc = gamma.numel()
+    l = _lib.load()
+    _lib.check(l.b200v_groupnorm_stats(x.data_ptr(), x.stride(0), frames, tokens_per_frame, Cc, groups,
+                                       frames_per_stat, sums.data_ptr(), _stream()), "b200v_groupnorm_stats")
+    _lib.check(l.b200v_groupnorm_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), frames,
+                                       tokens_per_frame, Cc, groups, frames_per_stat, sums.data_ptr(),
+                                       gamma.data_ptr(), beta.data_ptr(), eps, int(silu), _stream()),
+               "b200v_groupnorm_apply")
+    return y
+
+
+def layernorm(x, y, gamma, beta, eps: float = 1e-5, addvec=None, av_div: int = 1, av_mod: int = 1):
+    tokens, ldx = _rows(x)
+    _lib.check(_lib.load().b200v_layernorm(x.data_ptr(), ldx, y.data_ptr(), y.stride(0), tokens, gamma.numel(),
+                                           gamma.data_ptr(), beta.data_ptr(), eps, _ptr(addvec),
+                                           addvec.stride(0) if addvec is not None else 0, av_div, av_mod,
+                                           _stream()), "b200v_layernorm")
+    return y
+
+
+def conv3x3_small_cin(x8, cin: int, w, bias, out, NB: int, H: int, W: int):
+    _lib.check(_lib.load().b200v_conv3x3_small_cin(x8.data_ptr(), cin, w.data_ptr(), _ptr(bias), out.data_ptr(),
+                                                   out.stride(0), NB, H, W, w.shape[0], _stream()),
+               "b200v_conv3x3_small_cin")
+    return out
+
+
+def conv3x3_small_cout(x, w, bias, out, NB: int, H: int, W: int):
+    _lib.check(_lib.load().b200v_conv3x3_small_cout(x.data_ptr(), x.stride(0), w.shape[1], w.data_ptr(), _ptr(bias),
+                                                    out.data_ptr(), NB, H, W, w.shape[0], _stream()),
+               "b200v_conv3x3_small_cout")
+    return out
+
+
+def im2col_s2(x, out, NB: int, H: int, W: int, Cc: int):
+    _lib.check(_lib.load().b200v_im2col_s2(x.data_ptr(), x.stride(0), out.data_ptr(), NB, H, W, Cc, _stream()),
+               "b200v_im2col_s2")
+    return out
+
+
+def upsample2x(x, out, NB: int, H: int, W: int, Cc: int):
+    _lib.check(_lib.load().b200v_upsample2x(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), NB, H, W, Cc,
+                                            _stream()), "b200v_upsample2x")
+    return out
+
+
+def timestep_embedding(t, out, dim: int, max_period: float = 10000.0):
+    _lib.check(_lib.load().b200v_timestep_embedding(t.data_ptr(), t.numel(), dim, max_period, out.data_ptr(),
+                                                    out.stride(0), _stream()), "b200v_timestep_embedding")
+    return out
+
+
+def blend_emb(e_plain, e_cond, label, mask, emb, silu_emb):
+    rows, dim = e_plain.shape
+    _lib.check(_lib.load().b200v_blend_emb(e_plain.data_ptr(), _ptr(e_cond), _ptr(label), _ptr(mask), _ptr(emb),
+                                           _ptr(silu_emb), rows, dim, _stream()), "b200v_blend_emb")
+
+
+def sampler_prepare(x, cond_frame, mask, concat_c, sigmas, step_idx, unet_in, c_noise, T, h, w):
+    _lib.check(_lib.load().b200v_sampler_prepare(x.data_ptr(), _ptr(cond_frame), _ptr(mask), _ptr(concat_c),
+                                                 sigmas.data_ptr(), step_idx.data_ptr(), unet_in.data_ptr(),
+                                                 _ptr(c_noise), T, h, w, _stream()), "b200v_sampler_prepare")
+
+
+def sampler_update(x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_steps, T, h, w):
+    _lib.check(_lib.load().b200v_sampler_update(x.data_ptr(), net_out.data_ptr(), _ptr(cond_frame), _ptr(mask),
+                                                scales.data_ptr(), sigmas.data_ptr(), step_idx.data_ptr(), num_steps,
+                                                T, h, w, _stream()), "b200v_sampler_update")
+
+
+def nchw_to_tokens(x, out, NB, Cc, H, W):
+    _lib.check(_lib.load().b200v_nchw_to_tokens(x.data_ptr(), out.data_ptr(), out.stride(0), NB, Cc, H, W, _stream()),
+               "b200v_nchw_to_tokens")
+    return out
+
+
+def tokens_to_nchw(x, out, NB, Cc, H, W):
+    _lib.check(_lib.load().b200v_tokens_to_nchw(x.data_ptr(), int(x.dtype == torch.float32), x.stride(0),
+                                                out.data_ptr(), NB, Cc, H, W, _stream()), "b200v_tokens_to_nchw")
+    return out
