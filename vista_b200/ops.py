@@ -18,6 +18,14 @@ TAPS_T3 = [(-1, 0), (0, 0), (1, 0)]                              # (3,1,1) conv:
 TAPS_1 = [(0, 0)]
 
 
+LAUNCHES = 0   # kernels of this library launched so far (bench.py reports the per-step delta)
+
+
+def _count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -101,11 +109,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
     if res2 is not None:
         d.res2, d.ld_res2, d.s_res2 = res2.data_ptr(), res2.stride(0), s_res2
     d.s_acc = s_acc
+    _count()
     _lib.check(_lib.load().b200v_gemm(C.byref(d), _stream()), "b200v_gemm")
     return out
 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int):
+    _count(1)
     _lib.check(_lib.load().b200v_attention_spatial(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
                                                    v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
                                                    frames, seq, heads, _stream()), "b200v_attention_spatial")
@@ -113,6 +123,7 @@ def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int):
 
 
 def attention_temporal(q, k, v, out, nb: int, T: int, S: int, heads: int):
+    _count(1)
     _lib.check(_lib.load().b200v_attention_temporal(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
                                                     v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
                                                     nb, T, S, heads, _stream()), "b200v_attention_temporal")
@@ -124,6 +135,7 @@ def groupnorm(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float,
     """Two-phase GroupNorm; ``sums`` ([frames/frames_per_stat, groups, 2] fp64) must be zero on entry."""
     Cc = gamma.numel()
     l = _lib.load()
+    _count(2)
     _lib.check(l.b200v_groupnorm_stats(x.data_ptr(), x.stride(0), frames, tokens_per_frame, Cc, groups,
                                        frames_per_stat, sums.data_ptr(), _stream()), "b200v_groupnorm_stats")
     _lib.check(l.b200v_groupnorm_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), frames,
@@ -135,6 +147,7 @@ def groupnorm(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float,
 
 def layernorm(x, y, gamma, beta, eps: float = 1e-5, addvec=None, av_div: int = 1, av_mod: int = 1):
     tokens, ldx = _rows(x)
+    _count(1)
     _lib.check(_lib.load().b200v_layernorm(x.data_ptr(), ldx, y.data_ptr(), y.stride(0), tokens, gamma.numel(),
                                            gamma.data_ptr(), beta.data_ptr(), eps, _ptr(addvec),
                                            addvec.stride(0) if addvec is not None else 0, av_div, av_mod,
@@ -143,6 +156,7 @@ def layernorm(x, y, gamma, beta, eps: float = 1e-5, addvec=None, av_div: int = 1
 
 
 def conv3x3_small_cin(x8, cin: int, w, bias, out, NB: int, H: int, W: int):
+    _count(1)
     _lib.check(_lib.load().b200v_conv3x3_small_cin(x8.data_ptr(), cin, w.data_ptr(), _ptr(bias), out.data_ptr(),
                                                    out.stride(0), NB, H, W, w.shape[0], _stream()),
                "b200v_conv3x3_small_cin")
@@ -150,6 +164,7 @@ def conv3x3_small_cin(x8, cin: int, w, bias, out, NB: int, H: int, W: int):
 
 
 def conv3x3_small_cout(x, w, bias, out, NB: int, H: int, W: int):
+    _count(1)
     _lib.check(_lib.load().b200v_conv3x3_small_cout(x.data_ptr(), x.stride(0), w.shape[1], w.data_ptr(), _ptr(bias),
                                                     out.data_ptr(), NB, H, W, w.shape[0], _stream()),
                "b200v_conv3x3_small_cout")
@@ -157,18 +172,21 @@ def conv3x3_small_cout(x, w, bias, out, NB: int, H: int, W: int):
 
 
 def im2col_s2(x, out, NB: int, H: int, W: int, Cc: int):
+    _count(1)
     _lib.check(_lib.load().b200v_im2col_s2(x.data_ptr(), x.stride(0), out.data_ptr(), NB, H, W, Cc, _stream()),
                "b200v_im2col_s2")
     return out
 
 
 def upsample2x(x, out, NB: int, H: int, W: int, Cc: int):
+    _count(1)
     _lib.check(_lib.load().b200v_upsample2x(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), NB, H, W, Cc,
                                             _stream()), "b200v_upsample2x")
     return out
 
 
 def timestep_embedding(t, out, dim: int, max_period: float = 10000.0):
+    _count(1)
     _lib.check(_lib.load().b200v_timestep_embedding(t.data_ptr(), t.numel(), dim, max_period, out.data_ptr(),
                                                     out.stride(0), _stream()), "b200v_timestep_embedding")
     return out
@@ -176,29 +194,34 @@ def timestep_embedding(t, out, dim: int, max_period: float = 10000.0):
 
 def blend_emb(e_plain, e_cond, label, mask, emb, silu_emb):
     rows, dim = e_plain.shape
+    _count(1)
     _lib.check(_lib.load().b200v_blend_emb(e_plain.data_ptr(), _ptr(e_cond), _ptr(label), _ptr(mask), _ptr(emb),
                                            _ptr(silu_emb), rows, dim, _stream()), "b200v_blend_emb")
 
 
 def sampler_prepare(x, cond_frame, mask, concat_c, sigmas, step_idx, unet_in, c_noise, T, h, w):
+    _count(1)
     _lib.check(_lib.load().b200v_sampler_prepare(x.data_ptr(), _ptr(cond_frame), _ptr(mask), _ptr(concat_c),
                                                  sigmas.data_ptr(), step_idx.data_ptr(), unet_in.data_ptr(),
                                                  _ptr(c_noise), T, h, w, _stream()), "b200v_sampler_prepare")
 
 
 def sampler_update(x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_steps, T, h, w):
+    _count(2)
     _lib.check(_lib.load().b200v_sampler_update(x.data_ptr(), net_out.data_ptr(), _ptr(cond_frame), _ptr(mask),
                                                 scales.data_ptr(), sigmas.data_ptr(), step_idx.data_ptr(), num_steps,
                                                 T, h, w, _stream()), "b200v_sampler_update")
 
 
 def nchw_to_tokens(x, out, NB, Cc, H, W):
+    _count(1)
     _lib.check(_lib.load().b200v_nchw_to_tokens(x.data_ptr(), out.data_ptr(), out.stride(0), NB, Cc, H, W, _stream()),
                "b200v_nchw_to_tokens")
     return out
 
 
 def tokens_to_nchw(x, out, NB, Cc, H, W):
+    _count(1)
     _lib.check(_lib.load().b200v_tokens_to_nchw(x.data_ptr(), int(x.dtype == torch.float32), x.stride(0),
                                                 out.data_ptr(), NB, Cc, H, W, _stream()), "b200v_tokens_to_nchw")
     return out
