@@ -151,8 +151,9 @@ int b200v_blend_emb(const float* e_plain, const float* e_cond, const float* labe
  * sigma values are read from the device array `sigmas` at index *step_idx (device int); update
  * increments *step_idx so that a captured CUDA graph can be replayed for every step.
  * ---------------------------------------------------------------------------------------------- */
-int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask, const float* concat_c /* (T,4,h,w) or NULL */,
-                          const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
+int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask,
+                          const float* concat_u /* uncond rows (T,4,h,w) or NULL = zeros */,
+                          const float* concat_c /* cond rows (T,4,h,w) or NULL = zeros */, const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
                           int32_t T, int32_t h, int32_t w, void* stream);
 int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, 4] fp32 token-major */, const float* cond_frame,
                          const float* mask, const float* scales /* [T] */, const float* sigmas, int32_t* step_idx,

@@ -296,7 +296,7 @@ def test_sampler_step_kernels(ops):
     c_noise = torch.empty(2 * T, device=dev())
     xr = x0.clone()
     for i in range(steps):
-        ops.sampler_prepare(x, z, mask, concat, sig, step, unet_in, c_noise, T, h, w)
+        ops.sampler_prepare(x, z, mask, None, concat, sig, step, unet_in, c_noise, T, h, w)
         torch.cuda.synchronize()
         m = mask[:, None, None, None]
         xr = xr * (1 - m) + z * m

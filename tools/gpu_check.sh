@@ -11,6 +11,7 @@ run() {
   echo "${name} rc=$?  $(tail -n 1 gpurun_out/t_${name}.log)" >> gpurun_out/summary.txt
 }
 F=tests/test_kernels_gpu.py
+if [ -z "$SKIP_KERNELS" ]; then
 run gemm_plain   $F -k "gemm_linear_plain"
 run gemm_epi     $F -k "gemm_epilogue or gemm_silu or gemm_geglu"
 run gemm_conv    $F -k "gemm_conv3x3"
@@ -19,10 +20,11 @@ run attn_sp      $F -k "attention_spatial"
 run attn_t       $F -k "attention_temporal"
 run norms        $F -k "groupnorm or layernorm"
 run small        $F -k "small or upsample or timestep or layout or sampler"
-for extra in "$@"; do run "extra_$(basename $extra .py)" "$extra"; done
+fi
+for extra in "$@"; do run "extra_$(basename $extra .py)" "$extra" -s; done
 cat gpurun_out/summary.txt
 # bring-up aid: if spatial attention failed, try the alternative V-descriptor stride assignments
-if ! grep -q "attn_sp rc=0" gpurun_out/summary.txt; then
+if [ -z "$SKIP_KERNELS" ] && ! grep -q "attn_sp rc=0" gpurun_out/summary.txt; then
   for v in "1024 16384 2048" "1024 1024 2048" "16384 1024 1024"; do
     set -- $v
     VB_DBG_V_LBO=$1 VB_DBG_V_SBO=$2 VB_DBG_V_KSTEP=$3 timeout 300 python -m pytest -q --no-header -p no:cacheprovider \

@@ -444,8 +444,8 @@ __global__ void blend_emb_kernel(const float* __restrict__ e_plain, const float*
 // ------------------------------------------------------------------------------------------
 // one thread per latent pixel (t, y, x); handles the 4 channels
 __global__ void sampler_prepare_kernel(float* __restrict__ x, const float* __restrict__ cond_frame,
-                                       const float* __restrict__ mask, const float* __restrict__ concat_c,
-                                       const float* __restrict__ sigmas, const int* __restrict__ step_idx,
+                                       const float* __restrict__ mask, const float* __restrict__ concat_u,
+                                       const float* __restrict__ concat_c, const float* __restrict__ sigmas, const int* __restrict__ step_idx,
                                        __half* __restrict__ unet_in, float* __restrict__ c_noise, int T, int h, int w) {
   const float sigma = sigmas[*step_idx];
   const float c_in = rsqrtf(sigma * sigma + 1.0f);
@@ -467,7 +467,7 @@ __global__ void sampler_prepare_kernel(float* __restrict__ x, const float* __res
     }
     xv[c] = v * c_in;
     cu[c] = xv[c];
-    xv[4 + c] = 0.f;                                   // uncond rows: concat zeroed (sample.py:243)
+    xv[4 + c] = concat_u ? concat_u[idx] : 0.f;        // uncond rows (zeros in sample.py:243)
     cu[4 + c] = concat_c ? concat_c[idx] : 0.f;        // cond rows
   }
   *reinterpret_cast<uint4*>(unet_in + ((long long)t * hw + pix) * 8) = f_to_h8(xv);
@@ -675,13 +675,13 @@ extern "C" int b200v_blend_emb(const float* e_plain, const float* e_cond, const 
   return 0;
 }
 
-extern "C" int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask, const float* concat_c,
-                                     const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
+extern "C" int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask, const float* concat_u,
+                                     const float* concat_c, const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
                                      int32_t T, int32_t h, int32_t w, void* stream) {
   VB_REQUIRE(x && sigmas && step_idx && unet_in_f16, "sampler_prepare: null pointer");
   const long long total = (long long)T * h * w;
   sampler_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, cond_frame, mask, concat_c, sigmas, step_idx, (__half*)unet_in_f16, c_noise, T, h, w);
+      x, cond_frame, mask, concat_u, concat_c, sigmas, step_idx, (__half*)unet_in_f16, c_noise, T, h, w);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

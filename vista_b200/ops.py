@@ -199,10 +199,10 @@ def blend_emb(e_plain, e_cond, label, mask, emb, silu_emb):
                                            _ptr(silu_emb), rows, dim, _stream()), "b200v_blend_emb")
 
 
-def sampler_prepare(x, cond_frame, mask, concat_c, sigmas, step_idx, unet_in, c_noise, T, h, w):
+def sampler_prepare(x, cond_frame, mask, concat_u, concat_c, sigmas, step_idx, unet_in, c_noise, T, h, w):
     _count(1)
-    _lib.check(_lib.load().b200v_sampler_prepare(x.data_ptr(), _ptr(cond_frame), _ptr(mask), _ptr(concat_c),
-                                                 sigmas.data_ptr(), step_idx.data_ptr(), unet_in.data_ptr(),
+    _lib.check(_lib.load().b200v_sampler_prepare(x.data_ptr(), _ptr(cond_frame), _ptr(mask), _ptr(concat_u),
+                                                 _ptr(concat_c), sigmas.data_ptr(), step_idx.data_ptr(), unet_in.data_ptr(),
                                                  _ptr(c_noise), T, h, w, _stream()), "b200v_sampler_prepare")
 
 

@@ -157,40 +157,43 @@ class UNetRuntime:
         rows = x16.shape[0]
         hmid = self.buf(f"{name}.mid", rows, l0.w.shape[0])
         self.gemm(x16, l0, hmid, act=1)
-        out = torch.empty(rows, l2.w.shape[0], dtype=torch.float32, device=self.dev)
+        out = self.buf(f"{name}.out", rows, l2.w.shape[0], torch.float32)
         self.gemm(hmid, l2, out)
         return out
 
-    def _attn2_const(self, W: dict, ctx16: torch.Tensor) -> torch.Tensor:
+    def _attn2_const(self, W: dict, ctx16: torch.Tensor, name: str) -> torch.Tensor:
         """to_out(to_v(ctx[:, :D]) + v_adapter(ctx[:, D:])) for a single-token context (attention.py:342-353,421)."""
         rows, D = ctx16.shape[0], self.cfg.context_dim
         Cc = W["v"].w.shape[0]
-        v = torch.empty(rows, Cc, dtype=torch.float16, device=self.dev)
+        v = self.buf("a2.v", rows, Cc)
         self.gemm(ctx16[:, :D], W["v"], v)
         if W["va"] is not None:
-            v2 = torch.empty_like(v)
+            v2 = self.buf("a2.v2", rows, Cc)
             self.gemm(ctx16[:, D:], W["va"], v2, res1=v)
             v = v2
-        out = torch.empty(rows, Cc, dtype=torch.float32, device=self.dev)
+        out = self.buf(name, rows, Cc, torch.float32)   # persistent: captured CUDA graphs read it
         self.gemm(v, W["out"], out)
         return out
 
     def set_conditioning(self, context: torch.Tensor, y: torch.Tensor):
         """context (B,1,3456) / y (B,768): everything that does not depend on sigma or the step."""
         T = self.T
-        ctx16 = context.reshape(context.shape[0], -1).to(self.dev, torch.float16).contiguous()
-        y16 = y.to(self.dev, torch.float16).contiguous()
-        B = ctx16.shape[0]
+        B = context.shape[0]
+        ctx16 = self.buf("cond.ctx", B, context.numel() // B)
+        ctx16.copy_(context.reshape(B, -1))
+        y16 = self.buf("cond.y", B, y.shape[-1])
+        y16.copy_(y)
         cond = dict(B=B, label=self._mlp(y16, *self.label_emb, "label"), sp={}, tm={}, pos={})
-        tctx16 = ctx16[::T].contiguous()                           # video_attention.py:256
+        tctx16 = self.buf("cond.tctx", B // T, ctx16.shape[1])
+        tctx16.copy_(ctx16[::T])                                   # video_attention.py:256
         frames = torch.arange(T, dtype=torch.float32, device=self.dev)
         for t in self.plan.transformers():
             L = self.layers[t.prefix]
-            cond["sp"][t.prefix] = self._attn2_const(L["attn2"], ctx16)
-            cond["tm"][t.prefix] = self._attn2_const(L["tattn2"], tctx16)
-            temb = torch.empty(T, t.ch, dtype=torch.float16, device=self.dev)
+            cond["sp"][t.prefix] = self._attn2_const(L["attn2"], ctx16, f"cond.sp.{t.prefix}")
+            cond["tm"][t.prefix] = self._attn2_const(L["tattn2"], tctx16, f"cond.tm.{t.prefix}")
+            temb = self.buf("cond.temb", T, t.ch)
             ops.timestep_embedding(frames, temb, t.ch)
-            cond["pos"][t.prefix] = self._mlp(temb, *L["pos"], f"pos{t.ch}")
+            cond["pos"][t.prefix] = self._mlp(temb, *L["pos"], f"cond.pos.{t.prefix}")
         self.cond = cond
 
     # ------------------------------------------------------------------ layers
