@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the Vista denoising hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config full|small]
+
+A bench "step" is ONE EDM/Euler sampler step of a 25-frame 576x1024 clip: sampler_prepare ->
+UNet forward on the CFG-doubled batch (50 x 8 x 72 x 128) -> sampler_update — the loop body of
+vwm/modules/diffusionmodules/sampling.py:104-121.  `ms_per_step` is the "UNet step ms" of
+BASELINE.json; `value` is "denoised frames/sec at 25x576x1024, 50 EDM steps" =
+25 / (50 * step_seconds + decode_seconds), with the 25-frame chunked VAE decode timed in the same
+run (reported as `decode_ms`; null until the decoder lands, in which case `value` is sampler-only and
+`config.decode` says so).  Synthetic seeded weights / inputs (no checkpoint offline).
+
+N > 1 (torchrun): the path shards over independent clips (one clip per rank, no data-path
+collective) -> weak scaling; value = frames of all ranks / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_STEP_TFLOP = 153.9          # algorithmic TFLOP per EDM step at B=50, 72x128 (SURVEY.md §8d / BASELINE.md §2)
+F_DEC_CHUNK_TFLOP = 97.202    # per 14-frame VideoDecoder call
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))),
+                    tflops_burst=float(d.get("bf16_tflops", 1590.0)), hbm=float(d.get("hbm_gbs", 6650.0)), src="measured")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------
+# problem construction
+# ---------------------------------------------------------------------------------------------
+def make_problem(config: str, device, seed=0):
+    from vista_b200 import spec
+    if config == "full":
+        ucfg, dcfg, h, w = spec.unet_preset("vista"), spec.decoder_preset("vista"), 72, 128
+    else:  # reduced smoke configuration (NOT a bench value; used by --config small for quick checks)
+        ucfg, dcfg, h, w = spec.unet_preset("small"), spec.decoder_preset("small"), 16, 32
+    g = torch.Generator(device=device).manual_seed(1234 + seed)
+
+    def rand_sd(specs):
+        sd = {}
+        for k, (shape, kind) in specs.items():
+            fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+            if kind in ("w", "wz"):
+                t = torch.randn(shape, generator=g, device=device) * ((0.8 if kind == "w" else 0.5) / fan_in ** 0.5)
+            elif kind == "b":
+                t = torch.randn(shape, generator=g, device=device) * 0.05
+            elif kind == "g":
+                t = 1 + 0.1 * torch.randn(shape, generator=g, device=device)
+            else:
+                t = (0.5 if kind == "mix" else 0.0) + 0.3 * torch.randn(shape, generator=g, device=device)
+            sd[k] = t
+        return sd
+
+    return ucfg, dcfg, h, w, rand_sd
+
+
+def host_inputs(ucfg, T, h, w, seed=7):
+    from vista_b200 import synth
+    c, uc = synth.synth_conditioning(seed, T, h, w, trajectory=True, context_dim=ucfg.context_dim, adm=ucfg.adm_in_channels)
+    noise, z, mask = synth.synth_latents(seed, T, h, w)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return ({k: pin(v) for k, v in c.items()}, {k: pin(v) for k, v in uc.items()}, pin(noise), pin(z), pin(mask))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from vista_b200 import lib, ops
+    from vista_b200.diffusion import B200Denoiser, Denoiser, EulerEDMSampler
+    from vista_b200.modules import B200Wrapper, VideoUNet, _infer_config
+    from vista_b200 import fused
+    lib.load()
+    T = 25
+    ucfg, dcfg, h, w, rand_sd = make_problem(args.config, dev, seed=rank)
+    # public-API objects (what sample_utils.init_model would build from the YAML)
+    with torch.device(dev):
+      unet = VideoUNet(in_channels=ucfg.in_channels, model_channels=ucfg.model_channels, out_channels=ucfg.out_channels,
+                     num_res_blocks=ucfg.num_res_blocks, attention_resolutions=list(ucfg.attention_resolutions),
+                     channel_mult=list(ucfg.channel_mult), num_head_channels=64, num_classes="sequential",
+                     context_dim=ucfg.context_dim, adm_in_channels=ucfg.adm_in_channels, extra_ff_mix_layer=True,
+                     use_spatial_context=True, merge_strategy="learned_with_images", video_kernel_size=[3, 1, 1],
+                     use_linear_in_transformer=True, action_control=True)
+    from vista_b200 import spec as _spec
+    unet.load_state_dict(rand_sd(_spec.unet_param_specs(ucfg)), strict=True)
+    net = B200Wrapper(unet)
+    denoiser = Denoiser({"target": "vista_b200.diffusion.VScalingWithEDMcNoise"}, num_frames=T)
+    K, W = args.steps, args.warmup
+    sampler = EulerEDMSampler(num_steps=50, device="cuda", s_churn=0.0, s_tmin=0.0, s_tmax=999.0, s_noise=1.0, verbose=False,
+                              discretization_config={"target": "vista_b200.diffusion.EDMDiscretization",
+                                                     "params": {"sigma_min": 0.002, "sigma_max": 700.0, "rho": 7.0}},
+                              guider_config={"target": "vista_b200.diffusion.VanillaCFG", "params": {"scale": 2.5}})
+    bden = B200Denoiser(denoiser, net)
+    c_h, uc_h, noise_h, z_h, mask_h = host_inputs(ucfg, T, h, w)
+    to_dev = lambda d: {k: v.to(dev, non_blocking=True) for k, v in d.items()}
+
+    # ---- device-resident timing: K sampler steps (graph replays) bracketed by events
+    c, uc = to_dev(c_h), to_dev(uc_h)
+    noise, z, mask = noise_h.to(dev), z_h.to(dev), mask_h.to(dev)
+    rt = net._rt_get(unet, T, dev)
+    x = noise.clone()
+    sampler(bden, x, c, uc=uc, cond_frame=z, cond_mask=mask, num_steps=max(W, 3))   # warm-up: allocs + graph capture
+    st = rt._loop_states[(T, h, w)]
+    n_total = W + K
+    assert n_total + 1 <= st.sigmas.numel()
+    sig = sampler.discretization(n_total, device="cpu").to(torch.float32)
+    l0 = ops.LAUNCHES
+    st.one_step(rt, n_total)   # eager (counts launches of one step)
+    launches_per_step = ops.LAUNCHES - l0
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        st.one_step(rt, n_total)
+    st.x.copy_(noise * torch.sqrt(1.0 + sig[0] ** 2).to(dev))
+    st.sigmas[: n_total + 1].copy_(sig)
+    st.step.zero_()
+    for _ in range(W):
+        g.replay()
+    clocks = ClockSampler(local)
+    barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
+    barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    dt = e0.elapsed_time(e1) / 1e3
+    clk = clocks.stop()
+    finite = bool(torch.isfinite(st.x).all())
+
+    # ---- decode (not landed yet -> None)
+    decode_s = None
+    try:
+        from vista_b200.vae import bench_decode
+        decode_s = bench_decode(dcfg, rand_sd, dev, T, h, w)
+    except ImportError:
+        pass
+
+    # ---- e2e: the public call with HOST inputs / HOST result inside the timed region
+    def e2e_once(nsteps):
+        cc, ucc = to_dev(c_h), to_dev(uc_h)
+        xx = noise_h.to(dev, non_blocking=True)
+        zz, mm = z_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
+        out = sampler(bden, xx, cc, uc=ucc, cond_frame=zz, cond_mask=mm, num_steps=nsteps)
+        return out.to("cpu", non_blocking=False)
+    e2e_once(K)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = e2e_once(K)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    h2d = sum(v.numel() * v.element_size() for d in (c_h, uc_h) for v in d.values()) + \
+        sum(v.numel() * v.element_size() for v in (noise_h, z_h, mask_h))
+    d2h = res.numel() * res.element_size()
+
+    if world > 1:
+        tmax = torch.tensor([dt, e2e_dt], device=dev)
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        dt, e2e_dt = float(tmax[0]), float(tmax[1])
+    step_s = dt / K
+    e2e_step_s = e2e_dt / K
+
+    def fps(step_seconds):
+        total = 50 * step_seconds + (decode_s or 0.0)
+        return world * T / total
+
+    peaks = load_peaks()
+    full = args.config == "full"
+    ach = (F_STEP_TFLOP / step_s) if full else None
+    out = {
+        "metric": "denoised frames/sec at 25x576x1024, 50 EDM steps; UNet step ms",
+        "value": fps(step_s), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 (fp32 accumulate, fp32 norms/softmax/sampler state)", "data": "synthetic",
+        "config": {"workload": "configs[1]: full 50-step sample, 25x576x1024 (latent 25x4x72x128, CFG batch 50), 1 cond frame, "
+                               "VanillaCFG 2.5" if full else "REDUCED smoke config (not a bench value)",
+                   "step": "one EDM/Euler step (prepare + UNet + update); frames/s = 25/(50*step + decode)",
+                   "decode": "included" if decode_s is not None else "NOT IMPLEMENTED YET: value is sampler-only",
+                   "l2": "activations per step (> 10 GB) exceed the 126 MB L2; no explicit flush",
+                   "sharding": "one clip per rank, no data-path collective" if world > 1 else "single GPU"},
+        "decode_ms": None if decode_s is None else decode_s * 1e3,
+        "finite": finite,
+        "gpu_launches": launches_per_step * K,
+        "launches_per_step": launches_per_step,
+        "clocks": clk,
+        "e2e": {"value": fps(e2e_step_s), "unit": "frames/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                "ms_per_step": e2e_step_s * 1e3},
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": (ach / peaks["tflops"]) if ach else None, "traffic": None,
+                     "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
+                     "flops_per_step_T": F_STEP_TFLOP, "scope": "whole UNet step (all kernels)"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_step(h, w, threads):
+    """One EDM step (CFG batch 50) of the oracle (CPU fp32 restatement of the reference modules) with the
+    FULL vista architecture at a reduced latent size; returns seconds."""
+    from oracle import vista_oracle as vo
+    from vista_b200 import spec
+    torch.set_num_threads(threads)
+    cfg = spec.unet_preset("vista")
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for k, (shape, kind) in spec.unet_param_specs(cfg).items():
+        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+        sd[k] = torch.randn(shape, generator=g) * (0.5 / fan_in ** 0.5) if kind in ("w", "wz") else \
+            (torch.ones(shape) if kind == "g" else torch.full(shape, 0.3) if kind.startswith("mix") else torch.zeros(shape))
+    T = 25
+    from vista_b200 import synth
+    c, uc = synth.synth_conditioning(7, T, h, w)
+    noise, z, mask = synth.synth_latents(7, T, h, w)
+    tt = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        vo.euler_edm_sample(sd, cfg, torch.from_numpy(noise), tt(c), tt(uc), torch.from_numpy(z), torch.from_numpy(mask), 1, T)
+    return time.perf_counter() - t0
+
+
+def flops_scale(h, w):
+    """FLOPs(72x128) / FLOPs(h x w): linear in pixels except the spatial-attention core (quadratic)."""
+    full_lin, full_attn = F_STEP_TFLOP - 31.0, 31.0
+    r = (72 * 128) / (h * w)
+    small = full_lin / r + full_attn / (r * r)
+    return F_STEP_TFLOP / small
+
+
+def cpu_baseline(budget_s=20.0):
+    cores = os.cpu_count() or 1
+    h, w = 16, 32
+    t = cpu_sample_step(h, w, cores)
+    scale = flops_scale(h, w)
+    step_full = t * scale
+    return {"value": 25.0 / (50 * step_full), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"one EDM step (CFG batch 50, full vista.yaml UNet, fp32 torch CPU oracle) at latent 25x4x{h}x{w}: "
+                      f"{t:.2f} s; extrapolated to 72x128 by the FLOP ratio {scale:.1f} and to 50 steps; decode excluded",
+            "step_seconds_sample": t}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    h, w = 16, 32
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = cpu_sample_step(h, w, cores)
+        if i >= args.warmup:
+            times.append(t)
+        if sum(times) > 240:
+            break
+    t = float(np.mean(times))
+    scale = flops_scale(h, w)
+    v = 25.0 / (50 * t * scale)
+    out = {"impl": "reference", "metric": "denoised frames/sec at 25x576x1024, 50 EDM steps; UNet step ms", "value": v,
+           "unit": "frames/s", "n_gpus": world, "steps": len(times), "warmup": args.warmup, "ms_per_step": t * scale * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "configs[1] via a bounded CPU sample", "note": "reference modules cannot be installed "
+                      "(pure-Python repo with missing deps, no setup.py); the oracle port (validated against the real "
+                      "reference modules by tests/test_oracle_golden.py) is timed on the host cores"},
+           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                            "sample": f"EDM step at latent 25x4x{h}x{w}, {t:.2f} s/step, FLOP-scaled x{scale:.1f} to 72x128, x50 steps"},
+           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="full", choices=["full", "small"])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 1 if args.impl == "reference" else 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,7 @@ Shapes / conditioning layout follow SURVEY.md §8(d) "Synthetic inputs":
 """
 from __future__ import annotations
 
+import os
 import zlib
 from typing import Dict, Iterable, Optional, Tuple
 
@@ -48,8 +49,18 @@ def synth_param(seed: int, name: str, spec: ParamSpec) -> np.ndarray:
     raise KeyError(kind)
 
 
-def synth_state_dict(specs: Dict[str, ParamSpec], seed: int = 1, prefix: str = "") -> Dict[str, np.ndarray]:
-    return {prefix + k: synth_param(seed, k, v) for k, v in specs.items()}
+def synth_state_dict(specs: Dict[str, ParamSpec], seed: int = 1, prefix: str = "", threads: int = 0) -> Dict[str, np.ndarray]:
+    """Every tensor has its own (seed, name) stream, so generation order / threading cannot change the values."""
+    n = sum(int(np.prod(v[0])) for v in specs.values())
+    if threads <= 0:
+        threads = min(16, os.cpu_count() or 1) if n > 50_000_000 else 1
+    if threads == 1:
+        return {prefix + k: synth_param(seed, k, v) for k, v in specs.items()}
+    from concurrent.futures import ThreadPoolExecutor
+    keys = list(specs)
+    with ThreadPoolExecutor(threads) as ex:
+        vals = list(ex.map(lambda k: synth_param(seed, k, specs[k]), keys))
+    return {prefix + k: v for k, v in zip(keys, vals)}
 
 
 def checksum(arrays: Iterable[np.ndarray]) -> str:
