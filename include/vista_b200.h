@@ -159,6 +159,19 @@ int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, 4] fp32 toke
                          const float* mask, const float* scales /* [T] */, const float* sigmas, int32_t* step_idx,
                          int32_t num_steps, int32_t T, int32_t h, int32_t w, void* stream);
 
+/* VAE decoder helpers.
+ *   softmax_rows : fp32 scores -> fp16 probabilities, one row per block (mid.attn_1 single-head d=512
+ *                  attention, vwm/modules/diffusionmodules/model.py:158-170, done as GEMM-softmax-GEMM)
+ *   time_mix_small: AE3DConv.time_mix_conv (3->3 channels, (3,1,1)), temporal_ae.py:83-97, writing NCHW
+ *                  fp32 frames [out_frame0 + t]; frames with blend[t] != 0 are averaged with the existing
+ *                  content and frames t < skip_frames are dropped — the 3-frame chunk-overlap rule of
+ *                  DiffusionEngine.decode_first_stage (vwm/models/diffusion.py:166-170). */
+int b200v_softmax_rows(const float* x, int64_t ld_in, void* y_f16, int64_t ld_out, int64_t rows, int32_t cols,
+                       void* stream);
+int b200v_time_mix_small(const float* x /* [T*HW, C] fp32 */, const float* w /* [C,C,3] */, const float* bias,
+                         float* out /* NCHW fp32 */, const int32_t* blend, int32_t T, int32_t HW, int32_t C,
+                         int32_t out_frame0, int32_t skip_frames, void* stream);
+
 /* Layout converters at the boundary: NCHW fp32 <-> token-major (NHWC) fp16/fp32. */
 int b200v_nchw_to_tokens(const float* x, void* out_f16, int64_t ldo, int32_t NB, int32_t C, int32_t H, int32_t W,
                          void* stream);

@@ -715,3 +715,98 @@ extern "C" int b200v_tokens_to_nchw(const void* x, int32_t x_is_f32, int64_t ldx
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// VAE decoder helpers
+// ------------------------------------------------------------------------------------------
+namespace vb {
+
+// Row softmax: fp32 scores [rows, cols] (row stride ld_in) -> fp16 probabilities.  One block per row.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, long long ld_in, __half* __restrict__ y, long long ld_out, int cols) {
+  __shared__ float red[32];
+  const float* xr = x + (long long)blockIdx.x * ld_in;
+  __half* yr = y + (long long)blockIdx.x * ld_out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    __half2 a = __floats2half2_rn(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv);
+    __half2 b = __floats2half2_rn(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(yr + i) = u;
+  }
+}
+
+// AE3DConv's time_mix_conv (3 -> 3 channels, kernel (3,1,1), zero padded over frames) fused with the
+// chunk-overlap rule of decode_first_stage: frames with blend[t] != 0 are averaged with what `out`
+// already holds.  x: token-major fp32 [T*HW, C]; out: NCHW fp32 frames starting at out_frame0.
+__global__ void time_mix_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                      const float* __restrict__ bias, float* __restrict__ out, const int* __restrict__ blend,
+                                      int T, int HW, int C, int out_frame0, int skip_frames) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * HW) return;
+  const int t = (int)(i / HW), pix = (int)(i % HW);
+  if (t < skip_frames) return;
+  float acc[4];
+  for (int co = 0; co < C; ++co) acc[co] = bias ? bias[co] : 0.f;
+  for (int kt = 0; kt < 3; ++kt) {
+    const int tt = t + kt - 1;
+    if (tt < 0 || tt >= T) continue;
+    const float* xp = x + ((long long)tt * HW + pix) * C;
+    for (int ci = 0; ci < C; ++ci) {
+      const float xv = xp[ci];
+      for (int co = 0; co < C; ++co) acc[co] = fmaf(xv, w[(co * C + ci) * 3 + kt], acc[co]);
+    }
+  }
+  const int mode = blend ? blend[t] : 0;
+  for (int co = 0; co < C; ++co) {
+    float* op = out + ((long long)(out_frame0 + t) * C + co) * HW + pix;
+    *op = mode ? 0.5f * (*op + acc[co]) : acc[co];
+  }
+}
+
+}  // namespace vb
+
+extern "C" int b200v_softmax_rows(const float* x, int64_t ld_in, void* y_f16, int64_t ld_out, int64_t rows, int32_t cols,
+                                  void* stream) {
+  VB_REQUIRE(x && y_f16 && cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0, "softmax_rows: bad args");
+  vb::softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, ld_in, (__half*)y_f16, ld_out, cols);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_time_mix_small(const float* x, const float* w, const float* bias, float* out, const int32_t* blend,
+                                    int32_t T, int32_t HW, int32_t C, int32_t out_frame0, int32_t skip_frames,
+                                    void* stream) {
+  VB_REQUIRE(x && w && out && C >= 1 && C <= 4, "time_mix_small: bad args");
+  const long long total = (long long)T * HW;
+  vb::time_mix_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, w, bias, out, blend, T, HW, C, out_frame0, skip_frames);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

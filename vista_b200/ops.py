@@ -225,3 +225,18 @@ def tokens_to_nchw(x, out, NB, Cc, H, W):
     _lib.check(_lib.load().b200v_tokens_to_nchw(x.data_ptr(), int(x.dtype == torch.float32), x.stride(0),
                                                 out.data_ptr(), NB, Cc, H, W, _stream()), "b200v_tokens_to_nchw")
     return out
+
+
+def softmax_rows(x, y):
+    rows, cols = x.shape
+    _count(1)
+    _lib.check(_lib.load().b200v_softmax_rows(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), rows, cols, _stream()),
+               "b200v_softmax_rows")
+    return y
+
+
+def time_mix_small(x, w, bias, out, blend, T, HW, Cc, out_frame0=0, skip_frames=0):
+    _count(1)
+    _lib.check(_lib.load().b200v_time_mix_small(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(blend),
+                                                T, HW, Cc, out_frame0, skip_frames, _stream()), "b200v_time_mix_small")
+    return out

@@ -1,0 +1,271 @@
+"""B200 executor of the temporal VAE decoder and of the chunked ``decode_first_stage``.
+
+Reference behaviour (paths relative to the reference root):
+  VideoDecoder.forward ......... vwm/modules/diffusionmodules/model.py:664-694 + autoencoding/temporal_ae.py:105-151
+  decoder VideoResBlock ........ temporal_ae.py:55-72 on model.py:116-135 (GN eps 1e-6, swish); temporal
+                                 openaimodel.ResBlock with skip_t_emb (GN32 eps 1e-5); alpha*temporal + (1-alpha)*spatial
+  AttnBlock (1 head, d = C) .... model.py:147-176
+  AE3DConv ..................... temporal_ae.py:75-97
+  decode_first_stage ........... vwm/models/diffusion.py:150-180 (14-frame chunks, 3-frame overlap averaged)
+
+The reference runs this stage in fp32 (autocast disabled, configs/inference/vista.yaml:6); here the
+convolutions run on fp16 tensor cores with fp32 accumulation and fp32/fp64 normalisation statistics —
+the stated tolerance is in tests/test_decoder_gpu.py.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import register_param_tree
+from .spec import DecoderConfig, DecResBlockSpec, build_decoder_plan, decoder_param_specs
+from .unet import Lin
+from .weights import conv_weight_to_taps
+
+
+class DecoderRuntime:
+    def __init__(self, cfg: DecoderConfig, sd: Dict[str, torch.Tensor], device):
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.plan = build_decoder_plan(cfg)
+        self._bufs = {}
+        self._sd = sd
+        self._pack()
+        self._sd = None
+
+    # ------------------------------------------------------------------ packing
+    def _f32(self, name):
+        return self._sd[name].detach().to(self.dev, torch.float32).contiguous()
+
+    def _lin(self, prefix) -> Lin:
+        w = self._sd[f"{prefix}.weight"].detach().to(self.dev, torch.float32)
+        w = conv_weight_to_taps(w) if w.dim() > 2 else w
+        return Lin(w.to(torch.float16).contiguous(), self._f32(f"{prefix}.bias"), ops.pick_tile_n(w.shape[0]))
+
+    def _norm(self, prefix):
+        return self._f32(f"{prefix}.weight"), self._f32(f"{prefix}.bias")
+
+    def _pack(self):
+        sd = self._sd
+        self.n_gn = 0
+        self.res: Dict[str, dict] = {}
+
+        def pack_res(rb: DecResBlockSpec):
+            p, t = rb.prefix, f"{rb.prefix}.time_stack"
+            self.res[p] = dict(spec=rb, gn1=self._norm(f"{p}.norm1"), conv1=self._lin(f"{p}.conv1"),
+                               gn2=self._norm(f"{p}.norm2"), conv2=self._lin(f"{p}.conv2"),
+                               skip=self._lin(f"{p}.nin_shortcut") if rb.has_skip else None,
+                               tgn1=self._norm(f"{t}.in_layers.0"), tconv1=self._lin(f"{t}.in_layers.2"),
+                               tgn2=self._norm(f"{t}.out_layers.0"), tconv2=self._lin(f"{t}.out_layers.3"),
+                               alpha=float(torch.sigmoid(sd[f"{p}.mix_factor"].float()).item()), gn_idx=self.n_gn)
+            self.n_gn += 4
+
+        self.conv_in_w, self.conv_in_b = self._f32("conv_in.weight"), self._f32("conv_in.bias")
+        pack_res(self.plan.mid[0])
+        a = "mid.attn_1"
+        wq = self._lin(f"{a}.q")
+        self.attn = dict(norm=self._norm(f"{a}.norm"), q=wq, k=self._lin(f"{a}.k"),
+                         v_w=conv_weight_to_taps(sd[f"{a}.v.weight"].detach().to(self.dev, torch.float32)).to(torch.float16).contiguous(),
+                         v_b=self._f32(f"{a}.v.bias"), proj=self._lin(f"{a}.proj_out"), gn_idx=self.n_gn)
+        self.n_gn += 1
+        pack_res(self.plan.mid[1])
+        self.ups = {}
+        for blocks, up, ch in self.plan.levels:
+            for rb in blocks:
+                pack_res(rb)
+            if up is not None:
+                self.ups[up] = self._lin(up)
+        self.norm_out = self._norm("norm_out")
+        self.norm_out_idx = self.n_gn
+        self.n_gn += 1
+        self.out_w, self.out_b = self._f32("conv_out.weight"), self._f32("conv_out.bias")
+        self.tmix_w = self._f32("conv_out.time_mix_conv.weight").reshape(self.cfg.out_ch, self.cfg.out_ch, 3).contiguous()
+        self.tmix_b = self._f32("conv_out.time_mix_conv.bias")
+
+    # ------------------------------------------------------------------ helpers
+    def buf(self, name, rows, cols, dtype=torch.float16):
+        key = (name, rows, cols, dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = torch.empty(rows, cols, dtype=dtype, device=self.dev)
+        return t
+
+    def gemm(self, a, lin: Lin, out, **kw):
+        return ops.gemm(a, lin.w, out, bias=lin.b, tile_n=lin.tile_n, **kw)
+
+    def _gn(self, x, y, T, hw, norm, eps, idx, fps=1):
+        return ops.groupnorm(x, y, T, hw, norm[0], norm[1], eps, True, self.gn_sums[idx, : T // fps],
+                             frames_per_stat=fps, groups=self.cfg.num_groups)
+
+    def _resblock(self, L, x, T, h, w, name):
+        rb: DecResBlockSpec = L["spec"]
+        hw, M, gi = h * w, T * h * w, L["gn_idx"]
+        a1 = self._gn(x, self.buf("d.a1", M, rb.cin), T, hw, L["gn1"], 1e-6, gi)
+        h1 = self.gemm(a1, L["conv1"], self.buf("d.h1", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, T))
+        a2 = self._gn(h1, self.buf("d.a2", M, rb.cout), T, hw, L["gn2"], 1e-6, gi + 1)
+        xs = x if L["skip"] is None else self.gemm(x, L["skip"], self.buf("d.xs", M, rb.cout))
+        xsp = self.gemm(a2, L["conv2"], self.buf("d.xsp", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, T), res1=xs)
+        a3 = self._gn(xsp, self.buf("d.a1", M, rb.cout), T, hw, L["tgn1"], 1e-5, gi + 2, fps=T)
+        h2 = self.gemm(a3, L["tconv1"], self.buf("d.h1", M, rb.cout), taps=ops.TAPS_T3, geom=(hw, T, 1))
+        a4 = self._gn(h2, self.buf("d.a2", M, rb.cout), T, hw, L["tgn2"], 1e-5, gi + 3, fps=T)
+        # alpha*(xsp + conv) + (1-alpha)*xsp = xsp + alpha*(conv + bias)            (temporal_ae.py:68-69)
+        out = self.buf(name, M, rb.cout)
+        self.gemm(a4, L["tconv2"], out, taps=ops.TAPS_T3, geom=(hw, T, 1), s_acc=L["alpha"], res1=xsp)
+        return out
+
+    def _attn(self, x, T, h, w):
+        """GN -> q,k,v (1x1) -> softmax(q k^T / sqrt(C)) v -> proj_out -> + x, one head of dim C, per frame."""
+        A = self.attn
+        Cc, hw, M = x.shape[1], h * w, T * h * w
+        assert hw % 64 == 0, "decoder attention needs h*w to be a multiple of 64"
+        y = self.buf("d.attn_y", M, Cc)
+        xn = ops.groupnorm(x, self.buf("d.a1", M, Cc), T, hw, A["norm"][0], A["norm"][1], 1e-6, False,
+                           self.gn_sums[A["gn_idx"], :T], groups=self.cfg.num_groups)
+        q = self.gemm(xn, A["q"], self.buf("d.q", M, Cc))
+        k = self.gemm(xn, A["k"], self.buf("d.k", M, Cc))
+        o = self.buf("d.o", M, Cc)
+        s = self.buf("d.s", hw, hw, torch.float32)
+        p = self.buf("d.p", hw, hw)
+        vT = self.buf("d.vT", Cc, hw)
+        for f in range(T):
+            rows = slice(f * hw, (f + 1) * hw)
+            ops.gemm(A["v_w"], xn[rows], vT)         # V^T = W_v x^T; v bias is added after PV (softmax rows sum to 1)
+            ops.gemm(q[rows], k[rows], s, s_acc=float(Cc) ** -0.5)
+            ops.softmax_rows(s, p)
+            ops.gemm(p, vT, o[rows], bias=A["v_b"])
+        self.gemm(o, A["proj"], y, res1=x)
+        return y
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, z_tokens: torch.Tensor, T: int, h: int, w: int, out: torch.Tensor, out_frame0: int = 0,
+                blend: Optional[torch.Tensor] = None, skip_frames: int = 0) -> torch.Tensor:
+        """z_tokens: [(T h w), 8] fp16 (channels >= z_channels zero).  Writes frames
+        out[out_frame0 + skip_frames : out_frame0 + T] (NCHW fp32, (n,3,8h,8w))."""
+        cfg = self.cfg
+        if not hasattr(self, "gn_sums") or self.gn_sums.shape[1] < T:
+            self.gn_sums = torch.zeros(self.n_gn, T, cfg.num_groups, 2, dtype=torch.float64, device=self.dev)
+        self.gn_sums.zero_()
+        M = T * h * w
+        x = ops.conv3x3_small_cin(z_tokens, cfg.z_channels, self.conv_in_w, self.conv_in_b,
+                                  self.buf("d.in", M, self.plan.block_in), T, h, w)
+        x = self._resblock(self.res[self.plan.mid[0].prefix], x, T, h, w, "d.r0")
+        x = self._attn(x, T, h, w)
+        x = self._resblock(self.res[self.plan.mid[1].prefix], x, T, h, w, "d.r1")
+        for li, (blocks, up, ch) in enumerate(self.plan.levels):
+            for bi, rb in enumerate(blocks):
+                x = self._resblock(self.res[rb.prefix], x, T, h, w, f"d.r{bi % 2}")
+            if up is not None:
+                xu = ops.upsample2x(x, self.buf("d.up", T * 4 * h * w, ch), T, h, w, ch)
+                h, w = 2 * h, 2 * w
+                x = self.gemm(xu, self.ups[up], self.buf("d.upc", T * h * w, ch), taps=ops.TAPS_3X3, geom=(w, h, T))
+        M = T * h * w
+        a = ops.groupnorm(x, self.buf("d.a1", M, self.plan.final_ch), T, h * w, self.norm_out[0], self.norm_out[1], 1e-6,
+                          True, self.gn_sums[self.norm_out_idx, :T], groups=cfg.num_groups)
+        y = ops.conv3x3_small_cout(a, self.out_w, self.out_b, self.buf("d.y", M, cfg.out_ch, torch.float32), T, h, w)
+        ops.time_mix_small(y, self.tmix_w, self.tmix_b, out, blend, T, h * w, cfg.out_ch, out_frame0, skip_frames)
+        return out
+
+
+def decode_first_stage(rt: DecoderRuntime, z: torch.Tensor, scale_factor: float = 0.18215, n_samples: Optional[int] = 14,
+                       overlap: int = 3) -> torch.Tensor:
+    """vwm/models/diffusion.py:150-180 on the B200 decoder.  z: (F,4,h,w) fp32 -> (F,3,8h,8w) fp32."""
+    F_, zc, h, w = z.shape
+    n_samples = F_ if n_samples is None else n_samples
+    up = 2 ** (len(rt.cfg.ch_mult) - 1)
+    out = torch.empty(F_, rt.cfg.out_ch, h * up, w * up, dtype=torch.float32, device=z.device)
+    zs = (z.float() / scale_factor).contiguous()
+
+    def run(frames: torch.Tensor, out_frame0: int, n_overlap: int):
+        T = frames.shape[0]
+        tok = rt.buf("d.z", T * h * w, 8)
+        tok.zero_()
+        ops.nchw_to_tokens(frames.contiguous(), tok, T, zc, h, w)
+        blend = None
+        if n_overlap:
+            blend = torch.zeros(T, dtype=torch.int32, device=z.device)
+            blend[:n_overlap] = 1
+        rt.forward(tok, T, h, w, out, out_frame0=out_frame0, blend=blend)
+
+    if overlap < n_samples:
+        prev = zs[:overlap]
+        pos = overlap
+        first = True
+        for cur in zs[overlap:].split(n_samples - overlap, dim=0):
+            ctx = torch.cat((prev, cur), dim=0)
+            prev = cur[-overlap:]
+            run(ctx, pos - overlap, 0 if first else overlap)
+            pos += cur.shape[0]
+            first = False
+    else:
+        pos = 0
+        for cur in zs.split(n_samples, dim=0):
+            run(cur, pos, 0)
+            pos += cur.shape[0]
+    return out
+
+
+class VideoDecoder(nn.Module):
+    """``decoder_config.target`` stand-in for vwm.modules.autoencoding.temporal_ae.VideoDecoder: same keywords,
+    same ``state_dict`` keys, ``forward(z, timesteps=...)`` -> (n,3,8h,8w)."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions=(), dropout=0.0,
+                 resamp_with_conv=True, in_channels=3, resolution=256, z_channels=4, give_pre_end=False, tanh_out=False,
+                 use_linear_attn=False, attn_type="vanilla", video_kernel_size=3, alpha: float = 0.0,
+                 merge_strategy: str = "learned", time_mode: str = "conv-only", **ignorekwargs):
+        super().__init__()
+        vks = [3, 1, 1] if video_kernel_size is None else video_kernel_size
+        bad = [n for n, v in dict(attn_resolutions=len(list(attn_resolutions)) != 0, dropout=dropout != 0.0,
+                                  resamp_with_conv=not resamp_with_conv, give_pre_end=give_pre_end, tanh_out=tanh_out,
+                                  use_linear_attn=use_linear_attn, attn_type=attn_type != "vanilla",
+                                  video_kernel_size=isinstance(vks, int) or list(vks) != [3, 1, 1],
+                                  merge_strategy=merge_strategy != "learned", time_mode=time_mode != "conv-only").items() if v]
+        if bad:
+            raise NotImplementedError(f"vista_b200.VideoDecoder: unsupported option(s) {bad}")
+        self.b200_config = DecoderConfig(ch=ch, out_ch=out_ch, ch_mult=tuple(ch_mult), num_res_blocks=num_res_blocks,
+                                         z_channels=z_channels)
+        register_param_tree(self, decoder_param_specs(self.b200_config))
+        self._runtime = None
+        self.register_load_state_dict_post_hook(lambda module, keys: setattr(module, "_runtime", None))
+
+    def _apply(self, fn, *args, **kwargs):
+        self._runtime = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def runtime(self, device) -> DecoderRuntime:
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("vista_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self._runtime is None:
+            self._runtime = DecoderRuntime(self.b200_config, self.state_dict(), device)
+        return self._runtime
+
+    def forward(self, z: torch.Tensor, timesteps: Optional[int] = None, **kwargs) -> torch.Tensor:
+        rt = self.runtime(z.device)
+        T, zc, h, w = z.shape
+        assert timesteps in (None, T), "one clip per call (decode_first_stage passes timesteps == batch)"
+        up = 2 ** (len(rt.cfg.ch_mult) - 1)
+        out = torch.empty(T, rt.cfg.out_ch, h * up, w * up, dtype=torch.float32, device=z.device)
+        tok = rt.buf("d.z", T * h * w, 8)
+        tok.zero_()
+        ops.nchw_to_tokens(z.float().contiguous(), tok, T, zc, h, w)
+        return rt.forward(tok, T, h, w, out)
+
+    def get_last_layer(self, skip_time_mix=False, **kwargs):
+        return self.conv_out.time_mix_conv.weight if not skip_time_mix else self.conv_out.weight
+
+
+def bench_decode(dcfg: DecoderConfig, rand_sd, dev, T: int, h: int, w: int, reps: int = 1) -> float:
+    """Seconds for one chunked decode of a T-frame clip (warm)."""
+    sd = rand_sd(decoder_param_specs(dcfg))
+    rt = DecoderRuntime(dcfg, sd, dev)
+    z = torch.randn(T, dcfg.z_channels, h, w, device=dev) * 0.18215
+    decode_first_stage(rt, z)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        decode_first_stage(rt, z)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3 / reps
