@@ -26,6 +26,55 @@ def _count(n: int = 1):
     LAUNCHES += n
 
 
+TRACE = None   # debugging aid: set to a list to record (op, shape, checksum) after every launch (synchronises)
+
+
+def _trace(name: str, out: torch.Tensor):
+    if TRACE is not None:
+        torch.cuda.synchronize()
+        o = out.double()
+        TRACE.append((name, tuple(out.shape), float(o.sum()), float(o.abs().sum())))
+
+
+PROFILE = None   # set to a list: every launch is bracketed by CUDA events -> (family, detail, flops, bytes, ev0, ev1)
+_prof_open = None
+
+
+def _prof_begin(family: str, detail: str, flops: float, nbytes: float):
+    global _prof_open
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _prof_open = (family, detail, flops, nbytes, e0, e1)
+
+
+def _prof_end():
+    global _prof_open
+    if PROFILE is not None and _prof_open is not None:
+        _prof_open[5].record()
+        PROFILE.append(_prof_open)
+        _prof_open = None
+
+
+def profile_summary(records):
+    """Aggregates PROFILE records (after a synchronize) -> {family: dict(ms, launches, tflops, gbs)}, rows by detail."""
+    fam, det = {}, {}
+    for family, detail, flops, nbytes, e0, e1 in records:
+        ms = e0.elapsed_time(e1)
+        for table, key in ((fam, family), (det, (family, detail))):
+            r = table.setdefault(key, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+            r["ms"] += ms
+            r["launches"] += 1
+            r["flops"] += flops
+            r["bytes"] += nbytes
+    for table in (fam, det):
+        for r in table.values():
+            r["tflops"] = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else 0.0
+            r["gbs"] = r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else 0.0
+    return fam, det
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -110,23 +159,37 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
         d.res2, d.ld_res2, d.s_res2 = res2.data_ptr(), res2.stride(0), s_res2
     d.s_acc = s_acc
     _count()
+    n_out = N // 2 if act == 2 else N
+    _prof_begin("gemm", f"M={tokens} N={N} K={K} taps={ntaps} act={act}", 2.0 * tokens * N * K,
+                2.0 * tokens * cin + 2.0 * N * K + out.element_size() * tokens * n_out
+                + (2.0 * tokens * n_out if res1 is not None else 0) + (2.0 * tokens * n_out if res2 is not None else 0))
     _lib.check(_lib.load().b200v_gemm(C.byref(d), _stream()), "b200v_gemm")
+    _prof_end()
+    _trace(f"gemm taps={ntaps} act={act} N={N} K={K}", out)
     return out
 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int):
     _count(1)
+    _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
+                2.0 * 4 * frames * seq * heads * 64)
     _lib.check(_lib.load().b200v_attention_spatial(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
                                                    v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
                                                    frames, seq, heads, _stream()), "b200v_attention_spatial")
+    _prof_end()
+    _trace("attn_spatial", out)
     return out
 
 
 def attention_temporal(q, k, v, out, nb: int, T: int, S: int, heads: int):
     _count(1)
+    _prof_begin("attn_temporal", f"nb={nb} T={T} S={S} heads={heads}", 4.0 * 64 * heads * nb * S * T * T,
+                2.0 * 4 * nb * T * S * heads * 64)
     _lib.check(_lib.load().b200v_attention_temporal(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
                                                     v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
                                                     nb, T, S, heads, _stream()), "b200v_attention_temporal")
+    _prof_end()
+    _trace("attn_temporal", out)
     return out
 
 
@@ -136,107 +199,138 @@ def groupnorm(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float,
     Cc = gamma.numel()
     l = _lib.load()
     _count(2)
+    _prof_begin("groupnorm", f"tokens={frames * tokens_per_frame} C={Cc} fps={frames_per_stat}", 0.0,
+                2.0 * 3 * frames * tokens_per_frame * Cc)
     _lib.check(l.b200v_groupnorm_stats(x.data_ptr(), x.stride(0), frames, tokens_per_frame, Cc, groups,
                                        frames_per_stat, sums.data_ptr(), _stream()), "b200v_groupnorm_stats")
     _lib.check(l.b200v_groupnorm_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), frames,
                                        tokens_per_frame, Cc, groups, frames_per_stat, sums.data_ptr(),
                                        gamma.data_ptr(), beta.data_ptr(), eps, int(silu), _stream()),
                "b200v_groupnorm_apply")
+    _prof_end()
+    _trace(f"groupnorm fps={frames_per_stat}", y)
     return y
 
 
 def layernorm(x, y, gamma, beta, eps: float = 1e-5, addvec=None, av_div: int = 1, av_mod: int = 1):
     tokens, ldx = _rows(x)
     _count(1)
+    _prof_begin("layernorm", f"tokens={tokens} C={gamma.numel()}", 0.0, 2.0 * 2 * tokens * gamma.numel())
     _lib.check(_lib.load().b200v_layernorm(x.data_ptr(), ldx, y.data_ptr(), y.stride(0), tokens, gamma.numel(),
                                            gamma.data_ptr(), beta.data_ptr(), eps, _ptr(addvec),
                                            addvec.stride(0) if addvec is not None else 0, av_div, av_mod,
                                            _stream()), "b200v_layernorm")
+    _prof_end()
+    _trace("layernorm", y)
     return y
 
 
 def conv3x3_small_cin(x8, cin: int, w, bias, out, NB: int, H: int, W: int):
     _count(1)
+    _prof_begin("other", "conv3x3_small_cin", 0.0, 0.0)
     _lib.check(_lib.load().b200v_conv3x3_small_cin(x8.data_ptr(), cin, w.data_ptr(), _ptr(bias), out.data_ptr(),
                                                    out.stride(0), NB, H, W, w.shape[0], _stream()),
                "b200v_conv3x3_small_cin")
+    _prof_end()
     return out
 
 
 def conv3x3_small_cout(x, w, bias, out, NB: int, H: int, W: int):
     _count(1)
+    _prof_begin("other", "conv3x3_small_cout", 0.0, 0.0)
     _lib.check(_lib.load().b200v_conv3x3_small_cout(x.data_ptr(), x.stride(0), w.shape[1], w.data_ptr(), _ptr(bias),
                                                     out.data_ptr(), NB, H, W, w.shape[0], _stream()),
                "b200v_conv3x3_small_cout")
+    _prof_end()
     return out
 
 
 def im2col_s2(x, out, NB: int, H: int, W: int, Cc: int):
     _count(1)
+    _prof_begin("other", "im2col_s2", 0.0, 0.0)
     _lib.check(_lib.load().b200v_im2col_s2(x.data_ptr(), x.stride(0), out.data_ptr(), NB, H, W, Cc, _stream()),
                "b200v_im2col_s2")
+    _prof_end()
     return out
 
 
 def upsample2x(x, out, NB: int, H: int, W: int, Cc: int):
     _count(1)
+    _prof_begin("other", "upsample2x", 0.0, 0.0)
     _lib.check(_lib.load().b200v_upsample2x(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), NB, H, W, Cc,
                                             _stream()), "b200v_upsample2x")
+    _prof_end()
     return out
 
 
 def timestep_embedding(t, out, dim: int, max_period: float = 10000.0):
     _count(1)
+    _prof_begin("other", "timestep_embedding", 0.0, 0.0)
     _lib.check(_lib.load().b200v_timestep_embedding(t.data_ptr(), t.numel(), dim, max_period, out.data_ptr(),
                                                     out.stride(0), _stream()), "b200v_timestep_embedding")
+    _prof_end()
     return out
 
 
 def blend_emb(e_plain, e_cond, label, mask, emb, silu_emb):
     rows, dim = e_plain.shape
     _count(1)
+    _prof_begin("other", "blend_emb", 0.0, 0.0)
     _lib.check(_lib.load().b200v_blend_emb(e_plain.data_ptr(), _ptr(e_cond), _ptr(label), _ptr(mask), _ptr(emb),
                                            _ptr(silu_emb), rows, dim, _stream()), "b200v_blend_emb")
+    _prof_end()
 
 
 def sampler_prepare(x, cond_frame, mask, concat_u, concat_c, sigmas, step_idx, unet_in, c_noise, T, h, w):
     _count(1)
+    _prof_begin("other", "sampler_prepare", 0.0, 0.0)
     _lib.check(_lib.load().b200v_sampler_prepare(x.data_ptr(), _ptr(cond_frame), _ptr(mask), _ptr(concat_u),
                                                  _ptr(concat_c), sigmas.data_ptr(), step_idx.data_ptr(), unet_in.data_ptr(),
                                                  _ptr(c_noise), T, h, w, _stream()), "b200v_sampler_prepare")
+    _prof_end()
 
 
 def sampler_update(x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_steps, T, h, w):
     _count(2)
+    _prof_begin("other", "sampler_update", 0.0, 0.0)
     _lib.check(_lib.load().b200v_sampler_update(x.data_ptr(), net_out.data_ptr(), _ptr(cond_frame), _ptr(mask),
                                                 scales.data_ptr(), sigmas.data_ptr(), step_idx.data_ptr(), num_steps,
                                                 T, h, w, _stream()), "b200v_sampler_update")
+    _prof_end()
 
 
 def nchw_to_tokens(x, out, NB, Cc, H, W):
     _count(1)
+    _prof_begin("other", "nchw_to_tokens", 0.0, 0.0)
     _lib.check(_lib.load().b200v_nchw_to_tokens(x.data_ptr(), out.data_ptr(), out.stride(0), NB, Cc, H, W, _stream()),
                "b200v_nchw_to_tokens")
+    _prof_end()
     return out
 
 
 def tokens_to_nchw(x, out, NB, Cc, H, W):
     _count(1)
+    _prof_begin("other", "tokens_to_nchw", 0.0, 0.0)
     _lib.check(_lib.load().b200v_tokens_to_nchw(x.data_ptr(), int(x.dtype == torch.float32), x.stride(0),
                                                 out.data_ptr(), NB, Cc, H, W, _stream()), "b200v_tokens_to_nchw")
+    _prof_end()
     return out
 
 
 def softmax_rows(x, y):
     rows, cols = x.shape
     _count(1)
+    _prof_begin("other", "softmax_rows", 0.0, 0.0)
     _lib.check(_lib.load().b200v_softmax_rows(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), rows, cols, _stream()),
                "b200v_softmax_rows")
+    _prof_end()
     return y
 
 
 def time_mix_small(x, w, bias, out, blend, T, HW, Cc, out_frame0=0, skip_frames=0):
     _count(1)
+    _prof_begin("other", "time_mix_small", 0.0, 0.0)
     _lib.check(_lib.load().b200v_time_mix_small(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(blend),
                                                 T, HW, Cc, out_frame0, skip_frames, _stream()), "b200v_time_mix_small")
+    _prof_end()
     return out
