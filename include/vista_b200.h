@@ -95,18 +95,23 @@ int b200v_attention_temporal(const void* q, int64_t ld_q, const void* k, int64_t
                              void* out, int64_t ld_o, int32_t nb, int32_t T, int32_t S, int32_t heads, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * GroupNorm (32 groups) in two phases, fp32/fp64 statistics:
- *   stats: sums[stat, g, {sum, sumsq}] += over tokens of frames mapping to stat = frame / frames_per_stat
+ * GroupNorm (32 groups) in two phases, fp32 partials / fp64 reduction, bit-reproducible:
+ *   stats: per (frame, chunk of b200v_groupnorm_chunk() tokens, group) partial sums go to `partials`
+ *          ([frames * chunks * groups * 2] doubles of scratch); the last block of each statistic
+ *          (stat = frame / frames_per_stat, ticket in `counters`, which must be zero on first use and is
+ *          left zero) reduces them in a fixed order and writes mean_rstd[stat, group, {mean, rstd}].
  *   apply: y = (x - mean) * rstd * gamma + beta, optional SiLU, fp16 out
  * frames_per_stat = 1 is the per-frame GroupNorm32 (vwm/modules/diffusionmodules/util.py:214-216),
  * frames_per_stat = T is the (C/32, T, H, W) statistic of the temporal ResBlock
- * (video_model.py:67-72 with openaimodel.py:195-199, dims=3).  `sums` must be zeroed by the caller.
+ * (video_model.py:67-72 with openaimodel.py:195-199, dims=3).
  * ---------------------------------------------------------------------------------------------- */
+int b200v_groupnorm_chunk(void);
 int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C,
-                          int32_t groups, int32_t frames_per_stat, double* sums, void* stream);
+                          int32_t groups, int32_t frames_per_stat, float eps, double* partials, int32_t* counters,
+                          float* mean_rstd, void* stream);
 int b200v_groupnorm_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t frames, int32_t tokens_per_frame,
-                          int32_t C, int32_t groups, int32_t frames_per_stat, const double* sums, const float* gamma,
-                          const float* beta, float eps, int32_t silu, void* stream);
+                          int32_t C, int32_t groups, int32_t frames_per_stat, const float* mean_rstd, const float* gamma,
+                          const float* beta, int32_t silu, void* stream);
 
 /* LayerNorm over C per token (eps 1e-5), optional fp32 row-vector added to the input first:
  *   y = LN(x + addvec[(token/av_div)%av_mod, :]).   nn.LayerNorm at attention.py:488-490,

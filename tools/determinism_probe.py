@@ -31,8 +31,7 @@ twice("gemm conv3x3", lambda: ops.gemm(x, w9, out, taps=ops.TAPS_3X3, geom=(64, 
 gamma, beta = rnd(C, dt=torch.float32) * 0.1 + 1, rnd(C, dt=torch.float32) * 0.1
 y = torch.empty_like(x)
 def gn(fps):
-    sums = torch.zeros(50 // fps, 32, 2, dtype=torch.float64, device=dev)
-    return ops.groupnorm(x, y, 50, 36 * 64, gamma, beta, 1e-5, True, sums, frames_per_stat=fps)
+    return ops.groupnorm(x, y, 50, 36 * 64, gamma, beta, 1e-5, True, frames_per_stat=fps)
 twice("groupnorm per-frame", lambda: gn(1))
 twice("groupnorm temporal", lambda: gn(25))
 twice("layernorm", lambda: ops.layernorm(x, y, gamma, beta))

@@ -31,25 +31,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// GroupNorm statistics.  grid = (chunks, frames); a block walks `chunk` tokens of one frame; thread
-// (row, lane) owns the 8-channel vectors lane, lane+L, ... and keeps per-channel fp32 partials that
-// are reduced per group in shared memory and added to the fp64 global sums.
+// GroupNorm statistics, deterministic.  grid = (chunks, frames); a block walks `chunk` tokens of one
+// frame; thread (row, lane) owns the 8-channel vectors lane, lane+L, ... and keeps per-channel fp32
+// partials; rows are combined in a fixed order in shared memory, groups are summed in fp64 and written
+// as one partial per (frame, chunk, group).  The last block to finish a statistic (ticket counter)
+// adds the partials in a fixed order and writes (mean, rstd): bit-identical from run to run, no
+// floating-point atomics, no memset (the counter resets itself).
 // ------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxJ = 4;  // vectors per thread (C <= 8 * L * kGnMaxJ)
 
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_frame, int C, int groups,
-                int frames_per_stat, int chunk, int L, int J, double* __restrict__ sums) {
-  extern __shared__ float sh[];  // [2*C]
+                int frames_per_stat, int chunk, int L, int J, float eps, double* __restrict__ partials,
+                int* __restrict__ counters, float* __restrict__ mean_rstd) {
+  extern __shared__ float sh[];  // [rows][2*C]
+  __shared__ int s_last;
   const int frame = blockIdx.y;
   const int t0 = blockIdx.x * chunk;
   const int t1 = min(t0 + chunk, tokens_per_frame);
   const int nvec = C >> 3;
   const int rows = kGnThreads / L;
   const int lane = threadIdx.x % L, row = threadIdx.x / L;
-  for (int i = threadIdx.x; i < 2 * C; i += kGnThreads) sh[i] = 0.f;
-  __syncthreads();
   float s[kGnMaxJ][8], q[kGnMaxJ][8];
 #pragma unroll
   for (int j = 0; j < kGnMaxJ; ++j)
@@ -72,52 +75,77 @@ gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_fram
         }
       }
     }
+    float* mine = sh + (size_t)row * 2 * C;
 #pragma unroll
     for (int j = 0; j < kGnMaxJ; ++j) {
       const int v = lane + j * L;
       if (j < J && v < nvec) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          atomicAdd(&sh[v * 8 + i], s[j][i]);
-          atomicAdd(&sh[C + v * 8 + i], q[j][i]);
+          mine[v * 8 + i] = s[j][i];
+          mine[C + v * 8 + i] = q[j][i];
         }
       }
     }
   }
   __syncthreads();
   const int cpg = C / groups;
+  const int chunks = gridDim.x;
   for (int g = threadIdx.x; g < groups; g += kGnThreads) {
     double a = 0.0, b = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      a += (double)sh[c];
-      b += (double)sh[C + c];
+    for (int r = 0; r < rows; ++r) {
+      const float* p = sh + (size_t)r * 2 * C;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += (double)p[c];
+        b += (double)p[C + c];
+      }
     }
-    double* dst = sums + ((long long)(frame / frames_per_stat) * groups + g) * 2;
-    atomicAdd(dst, a);
-    atomicAdd(dst + 1, b);
+    double* dst = partials + (((long long)frame * chunks + blockIdx.x) * groups + g) * 2;
+    dst[0] = a;
+    dst[1] = b;
   }
+  __threadfence();
+  __syncthreads();
+  const int stat = frame / frames_per_stat;
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(&counters[stat], 1);
+    s_last = (ticket == frames_per_stat * chunks - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double cnt = (double)cpg * tokens_per_frame * frames_per_stat;
+  for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+    double a = 0.0, b = 0.0;
+    const double* src = partials + ((long long)stat * frames_per_stat * chunks * groups + g) * 2;
+    for (int i = 0; i < frames_per_stat * chunks; ++i) {
+      a += __ldcg(src + (long long)i * groups * 2);
+      b += __ldcg(src + (long long)i * groups * 2 + 1);
+    }
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[((long long)stat * groups + g) * 2] = (float)mean;
+    mean_rstd[((long long)stat * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  if (threadIdx.x == 0) counters[stat] = 0;  // ready for the next launch
 }
 
 // apply: grid = (chunks, frames); y = (x-mean)*rstd*gamma + beta, optional SiLU
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                 int tokens_per_frame, int C, int groups, int frames_per_stat, int chunk,
-                const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float eps, int silu) {
+                const float* __restrict__ mean_rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                int silu) {
   extern __shared__ float sh[];  // scale[C], shift[C]
   const int frame = blockIdx.y;
   const int cpg = C / groups;
-  const double cnt = (double)cpg * tokens_per_frame * frames_per_stat;
-  const double* st = sums + (long long)(frame / frames_per_stat) * groups * 2;
+  const float* st = mean_rstd + (long long)(frame / frames_per_stat) * groups * 2;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const double mean = st[2 * g] / cnt;
-    double var = st[2 * g + 1] / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = rstd * gamma[c];
+    const float sc = st[2 * g + 1] * gamma[c];
     sh[c] = sc;
-    sh[C + c] = beta[c] - (float)mean * sc;
+    sh[C + c] = beta[c] - st[2 * g] * sc;
   }
   __syncthreads();
   const int nvec = C >> 3;
@@ -548,8 +576,9 @@ static inline int grid_for(long long total, int block, int cap = 148 * 16) {
 using namespace vb;
 
 extern "C" int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C,
-                                     int32_t groups, int32_t frames_per_stat, double* sums, void* stream) {
-  VB_REQUIRE(x && sums, "groupnorm_stats: null pointer");
+                                     int32_t groups, int32_t frames_per_stat, float eps, double* partials,
+                                     int32_t* counters, float* mean_rstd, void* stream) {
+  VB_REQUIRE(x && partials && counters && mean_rstd, "groupnorm_stats: null pointer");
   VB_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0, "groupnorm_stats: C=%d groups=%d ldx=%lld invalid", C, groups,
              (long long)ldx);
   VB_REQUIRE(frames_per_stat > 0 && frames % frames_per_stat == 0, "groupnorm_stats: frames %% frames_per_stat != 0");
@@ -560,26 +589,37 @@ extern "C" int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames,
     L = (nvec + J - 1) / J;
   }
   VB_REQUIRE(J <= kGnMaxJ, "groupnorm_stats: C=%d too large", C);
-  const int chunk = 256;
+  const int rows = kGnThreads / L;
+  const int chunk = b200v_groupnorm_chunk();
   dim3 grid((tokens_per_frame + chunk - 1) / chunk, frames);
-  gn_stats_kernel<<<grid, kGnThreads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, tokens_per_frame, C, groups, frames_per_stat, chunk, L, J, sums);
+  const size_t smem = (size_t)rows * 2 * C * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  VB_REQUIRE(smem <= 160 * 1024, "groupnorm_stats: shared memory %zu too large", smem);
+  gn_stats_kernel<<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, tokens_per_frame, C, groups, frames_per_stat, chunk, L, J, eps, partials, counters,
+      mean_rstd);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+extern "C" int b200v_groupnorm_chunk(void) { return 256; }
+
 extern "C" int b200v_groupnorm_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t frames,
                                      int32_t tokens_per_frame, int32_t C, int32_t groups, int32_t frames_per_stat,
-                                     const double* sums, const float* gamma, const float* beta, float eps,
-                                     int32_t silu, void* stream) {
-  VB_REQUIRE(x && y && sums && gamma && beta, "groupnorm_apply: null pointer");
+                                     const float* mean_rstd, const float* gamma, const float* beta, int32_t silu,
+                                     void* stream) {
+  VB_REQUIRE(x && y && mean_rstd && gamma && beta, "groupnorm_apply: null pointer");
   VB_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_apply: bad C/ld");
   VB_REQUIRE(frames_per_stat > 0 && frames % frames_per_stat == 0, "groupnorm_apply: frames %% frames_per_stat != 0");
   const int chunk = 64;
   dim3 grid((tokens_per_frame + chunk - 1) / chunk, frames);
   gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, (__half*)y, ldy, tokens_per_frame, C, groups, frames_per_stat, chunk, sums, gamma, beta,
-      eps, silu);
+      (const __half*)x, ldx, (__half*)y, ldy, tokens_per_frame, C, groups, frames_per_stat, chunk, mean_rstd, gamma,
+      beta, silu);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -95,8 +95,9 @@ SIGNATURES = {
     "b200v_gemm": [C.POINTER(GemmDesc), _P],
     "b200v_attention_spatial": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
-    "b200v_groupnorm_stats": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P],
-    "b200v_groupnorm_apply": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _F, _I32, _P],
+    "b200v_groupnorm_chunk": [],
+    "b200v_groupnorm_stats": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _P],
+    "b200v_groupnorm_apply": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P],
     "b200v_layernorm": [_P, _I64, _P, _I64, _I64, _I32, _P, _P, _F, _P, _I64, _I32, _I32, _P],
     "b200v_conv3x3_small_cin": [_P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_conv3x3_small_cout": [_P, _I64, _I32, _P, _P, _P, _I32, _I32, _I32, _I32, _P],

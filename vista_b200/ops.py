@@ -193,19 +193,44 @@ def attention_temporal(q, k, v, out, nb: int, T: int, S: int, heads: int):
     return out
 
 
+class GNWorkspace:
+    """Scratch for the two-phase GroupNorm: partial sums (grown on demand) and self-resetting ticket counters."""
+
+    def __init__(self, device, max_stats: int = 4096):
+        self.device = device
+        self.partials = torch.empty(1 << 16, dtype=torch.float64, device=device)
+        self.counters = torch.zeros(max_stats, dtype=torch.int32, device=device)
+
+    def reserve(self, n_doubles: int):
+        if self.partials.numel() < n_doubles:
+            self.partials = torch.empty(n_doubles, dtype=torch.float64, device=self.device)
+
+
+_default_ws = {}
+
+
 def groupnorm(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float, silu: bool,
-              sums: torch.Tensor, frames_per_stat: int = 1, groups: int = 32):
-    """Two-phase GroupNorm; ``sums`` ([frames/frames_per_stat, groups, 2] fp64) must be zero on entry."""
+              stats: Optional[torch.Tensor] = None, frames_per_stat: int = 1, groups: int = 32,
+              ws: Optional[GNWorkspace] = None):
+    """Two-phase GroupNorm; ``stats`` ([frames/frames_per_stat, groups, 2] fp32) receives (mean, rstd)."""
     Cc = gamma.numel()
     l = _lib.load()
+    if ws is None:
+        ws = _default_ws.setdefault(x.device, GNWorkspace(x.device))
+    if stats is None:
+        stats = torch.empty(frames // frames_per_stat, groups, 2, dtype=torch.float32, device=x.device)
+    chunk = l.b200v_groupnorm_chunk()
+    ws.reserve(frames * (-(-tokens_per_frame // chunk)) * groups * 2)
+    assert frames // frames_per_stat <= ws.counters.numel()
     _count(2)
     _prof_begin("groupnorm", f"tokens={frames * tokens_per_frame} C={Cc} fps={frames_per_stat}", 0.0,
                 2.0 * 3 * frames * tokens_per_frame * Cc)
     _lib.check(l.b200v_groupnorm_stats(x.data_ptr(), x.stride(0), frames, tokens_per_frame, Cc, groups,
-                                       frames_per_stat, sums.data_ptr(), _stream()), "b200v_groupnorm_stats")
+                                       frames_per_stat, eps, ws.partials.data_ptr(), ws.counters.data_ptr(),
+                                       stats.data_ptr(), _stream()), "b200v_groupnorm_stats")
     _lib.check(l.b200v_groupnorm_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), frames,
-                                       tokens_per_frame, Cc, groups, frames_per_stat, sums.data_ptr(),
-                                       gamma.data_ptr(), beta.data_ptr(), eps, int(silu), _stream()),
+                                       tokens_per_frame, Cc, groups, frames_per_stat, stats.data_ptr(),
+                                       gamma.data_ptr(), beta.data_ptr(), int(silu), _stream()),
                "b200v_groupnorm_apply")
     _prof_end()
     _trace(f"groupnorm fps={frames_per_stat}", y)

@@ -145,9 +145,8 @@ class UNetRuntime:
         return ops.gemm(a, lin.w, out, bias=lin.b, tile_n=lin.tile_n, act=2 if lin.geglu else kw.pop("act", 0), **kw)
 
     def _gn(self, x, y, B, hw, norm, eps, silu, idx, fps=1):
-        sums = self.gn_sums[idx, : B // fps]
-        return ops.groupnorm(x, y, B, hw, norm[0], norm[1], eps, silu, sums, frames_per_stat=fps,
-                             groups=self.cfg.num_groups)
+        return ops.groupnorm(x, y, B, hw, norm[0], norm[1], eps, silu, self.gn_stats[idx, : B // fps],
+                             frames_per_stat=fps, groups=self.cfg.num_groups, ws=self.gn_ws)
 
     def _ln(self, x, y, norm, **kw):
         return ops.layernorm(x, y, norm[0], norm[1], 1e-5, **kw)
@@ -272,9 +271,10 @@ class UNetRuntime:
         B = c_noise.numel()
         assert B % T == 0 and x_tokens.shape[0] == B * h * w and self.cond["B"] == B
         mc, ed = cfg.model_channels, cfg.time_embed_dim
-        if not hasattr(self, "gn_sums") or self.gn_sums.shape[1] != B:
-            self.gn_sums = torch.zeros(self.n_gn, B, cfg.num_groups, 2, dtype=torch.float64, device=self.dev)
-        self.gn_sums.zero_()
+        if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] != B:
+            self.gn_stats = torch.zeros(self.n_gn, B, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+            self.gn_ws = ops.GNWorkspace(self.dev)
+            self.gn_ws.reserve(B * (-(-h * w // 256)) * cfg.num_groups * 2)
         # --- embeddings (video_model.py:456-471) + all emb_layers of the step in one GEMM
         temb = ops.timestep_embedding(c_noise, self.buf("emb.t", B, mc), mc)
         e_plain = self._mlp_step(temb, self.time_embed, "emb.plain")

@@ -96,8 +96,8 @@ class DecoderRuntime:
         return ops.gemm(a, lin.w, out, bias=lin.b, tile_n=lin.tile_n, **kw)
 
     def _gn(self, x, y, T, hw, norm, eps, idx, fps=1):
-        return ops.groupnorm(x, y, T, hw, norm[0], norm[1], eps, True, self.gn_sums[idx, : T // fps],
-                             frames_per_stat=fps, groups=self.cfg.num_groups)
+        return ops.groupnorm(x, y, T, hw, norm[0], norm[1], eps, True, self.gn_stats[idx, : T // fps],
+                             frames_per_stat=fps, groups=self.cfg.num_groups, ws=self.gn_ws)
 
     def _resblock(self, L, x, T, h, w, name):
         rb: DecResBlockSpec = L["spec"]
@@ -122,7 +122,7 @@ class DecoderRuntime:
         assert hw % 64 == 0, "decoder attention needs h*w to be a multiple of 64"
         y = self.buf("d.attn_y", M, Cc)
         xn = ops.groupnorm(x, self.buf("d.a1", M, Cc), T, hw, A["norm"][0], A["norm"][1], 1e-6, False,
-                           self.gn_sums[A["gn_idx"], :T], groups=self.cfg.num_groups)
+                           self.gn_stats[A["gn_idx"], :T], groups=self.cfg.num_groups, ws=self.gn_ws)
         q = self.gemm(xn, A["q"], self.buf("d.q", M, Cc))
         k = self.gemm(xn, A["k"], self.buf("d.k", M, Cc))
         o = self.buf("d.o", M, Cc)
@@ -144,9 +144,11 @@ class DecoderRuntime:
         """z_tokens: [(T h w), 8] fp16 (channels >= z_channels zero).  Writes frames
         out[out_frame0 + skip_frames : out_frame0 + T] (NCHW fp32, (n,3,8h,8w))."""
         cfg = self.cfg
-        if not hasattr(self, "gn_sums") or self.gn_sums.shape[1] < T:
-            self.gn_sums = torch.zeros(self.n_gn, T, cfg.num_groups, 2, dtype=torch.float64, device=self.dev)
-        self.gn_sums.zero_()
+        if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] < T:
+            self.gn_stats = torch.zeros(self.n_gn, T, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+            self.gn_ws = ops.GNWorkspace(self.dev)
+        up_total = 2 ** (len(cfg.ch_mult) - 1)
+        self.gn_ws.reserve(T * (-(-h * w * up_total * up_total // 256)) * cfg.num_groups * 2)
         M = T * h * w
         x = ops.conv3x3_small_cin(z_tokens, cfg.z_channels, self.conv_in_w, self.conv_in_b,
                                   self.buf("d.in", M, self.plan.block_in), T, h, w)
@@ -162,7 +164,7 @@ class DecoderRuntime:
                 x = self.gemm(xu, self.ups[up], self.buf("d.upc", T * h * w, ch), taps=ops.TAPS_3X3, geom=(w, h, T))
         M = T * h * w
         a = ops.groupnorm(x, self.buf("d.a1", M, self.plan.final_ch), T, h * w, self.norm_out[0], self.norm_out[1], 1e-6,
-                          True, self.gn_sums[self.norm_out_idx, :T], groups=cfg.num_groups)
+                          True, self.gn_stats[self.norm_out_idx, :T], groups=cfg.num_groups, ws=self.gn_ws)
         y = ops.conv3x3_small_cout(a, self.out_w, self.out_b, self.buf("d.y", M, cfg.out_ch, torch.float32), T, h, w)
         ops.time_mix_small(y, self.tmix_w, self.tmix_b, out, blend, T, h * w, cfg.out_ch, out_frame0, skip_frames)
         return out
