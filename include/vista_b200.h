@@ -160,8 +160,8 @@ int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask,
                           const float* concat_u /* uncond rows (T,4,h,w) or NULL = zeros */,
                           const float* concat_c /* cond rows (T,4,h,w) or NULL = zeros */, const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
                           int32_t T, int32_t h, int32_t w, void* stream);
-int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, 4] fp32 token-major */, const float* cond_frame,
-                         const float* mask, const float* scales /* [T] */, const float* sigmas, int32_t* step_idx,
+int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, ld_net] fp32 token-major, 4 channels used */,
+                         int64_t ld_net, const float* cond_frame, const float* mask, const float* scales /* [T] */, const float* sigmas, int32_t* step_idx,
                          int32_t num_steps, int32_t T, int32_t h, int32_t w, void* stream);
 
 /* VAE decoder helpers.
@@ -173,7 +173,8 @@ int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, 4] fp32 toke
  *                  DiffusionEngine.decode_first_stage (vwm/models/diffusion.py:166-170). */
 int b200v_softmax_rows(const float* x, int64_t ld_in, void* y_f16, int64_t ld_out, int64_t rows, int32_t cols,
                        void* stream);
-int b200v_time_mix_small(const float* x /* [T*HW, C] fp32 */, const float* w /* [C,C,3] */, const float* bias,
+int b200v_time_mix_small(const float* x /* [T*HW, ldx] fp32, C channels used */, int64_t ldx,
+                         const float* w /* [C,C,3] */, const float* bias,
                          float* out /* NCHW fp32 */, const int32_t* blend, int32_t T, int32_t HW, int32_t C,
                          int32_t out_frame0, int32_t skip_frames, void* stream);
 

@@ -109,6 +109,22 @@ def test_gemm_conv3x3(ops, NB, H, W, Cin, Cout):
     check(out.reshape(NB, H, W, Cout), ref.permute(0, 2, 3, 1), name="conv3x3")
 
 
+def test_gemm_conv3x3_thin_output_f32(ops):
+    """out[2] / decoder conv_out path: Cout padded to 8, fp32 output, tile_n 32."""
+    NB, H, W, Cin = 2, 9, 16, 320
+    x = rnd(NB, H, W, Cin, seed=51)
+    wt = torch.zeros(8, Cin, 3, 3, dtype=torch.float16, device=dev())
+    wt[:4] = rnd(4, Cin, 3, 3, seed=52, scale=(9 * Cin) ** -0.5)
+    bias = torch.zeros(8, device=dev())
+    bias[:4] = rnd(4, seed=53, dtype=torch.float32)
+    out = torch.full((NB * H * W, 8), 7.0, dtype=torch.float32, device=dev())
+    ops.gemm(x.reshape(-1, Cin), wt.permute(0, 2, 3, 1).reshape(8, 9 * Cin).contiguous(), out, taps=ops.TAPS_3X3,
+             geom=(W, H, NB), bias=bias, tile_n=32)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    check(out.reshape(NB, H, W, 8), ref, rtol=1e-3, atol=1e-3, name="thin conv")
+
+
 @pytest.mark.parametrize("nb,T,S,Cc", [(2, 25, 128, 64), (2, 25, 144, 128), (1, 14, 512, 64)])
 def test_gemm_temporal_conv(ops, nb, T, S, Cc):
     x = rnd(nb, T, S, Cc, seed=19)                        # tokens (b t) s

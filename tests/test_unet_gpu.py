@@ -30,7 +30,7 @@ def run_unet(preset, h, w, T, sigma=5.0):
     c_noise = torch.full((B,), 0.25 * float(np.log(sigma)), device=dev)
     out = rt.forward(tok, c_noise, torch.from_numpy(mask2).to(dev), h, w)
     res = torch.empty(B, cfg.out_channels, h, w, device=dev)
-    ops.tokens_to_nchw(out, res, B, cfg.out_channels, h, w)
+    ops.tokens_to_nchw(out, res, B, cfg.out_channels, h, w)   # out: [tokens, 8] fp32, first 4 used
     torch.cuda.synchronize()
     return res.cpu()
 

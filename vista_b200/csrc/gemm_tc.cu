@@ -72,52 +72,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf16) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Finishes 8 consecutive output columns of one token.
-__device__ __forceinline__ void finish8(const TGParams& p, float (&v)[8], long long token, int n_out, int n_bias,
-                                        int rv_row, bool valid) {
-  if (!valid) return;
-  if (p.bias) {
-    float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n_bias));
-    float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n_bias + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] *= p.s_acc;
-  if (p.rowvec) {
-    const float* rp = p.rowvec + (long long)rv_row * p.ld_rowvec + n_out;
-    float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-    float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-  }
-  if (p.act == 1) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
-  }
-  if (p.res1) {
-    float r[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) + token * p.ld_res1 + n_out)),
-            r, p.bf16);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += p.s_res1 * r[i];
-  }
-  if (p.res2) {
-    float r[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res2) + token * p.ld_res2 + n_out)),
-            r, p.bf16);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += p.s_res2 * r[i];
-  }
-  if (p.out_f32) {
-    float* op = reinterpret_cast<float*>(p.out) + token * p.ldo + n_out;
-    *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  } else {
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + token * p.ldo + n_out) = pack8(v, p.bf16);
-  }
-}
-
 __global__ void __launch_bounds__(192, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -222,73 +176,151 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 0..3)
+    // Phase A: thread = tile row (TMEM lane): accumulator -> (+bias)*s_acc + rowvec -> act / GEGLU, fp32,
+    //          written to a per-warp staging buffer (32 rows x 64 cols, 16-byte chunks XOR-swizzled by row).
+    // Phase B: the warp re-reads the buffer row-segment-wise so that residual loads and output stores are
+    //          128-byte contiguous per row (coalesced) instead of one 16-byte piece per row and instruction.
     int as = 0;
     uint32_t aphase = 0;
     const int r = warp * 32 + lane;  // row of the tile == TMEM lane
+    const uint32_t stg = smem_u32(stages + p.nstages * p.stage_bytes) + warp * (32 * 256);
+    const int half = p.TN >> 1;
+    const int tile_out_cols = (p.act == 2) ? half : p.TN;
+    const int n_out_total = (p.act == 2) ? (p.N >> 1) : p.N;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
-      long long token;
-      bool valid;
+      int token_own, valid_own;
       if (p.a_mode == 0) {
-        token = (long long)m_blk * 128 + r;
-        valid = token < p.tokens;
+        token_own = m_blk * 128 + r;
+        valid_own = token_own < p.tokens;
       } else {
         const int tw = m_blk % p.tiles_w;
         const int th = (m_blk / p.tiles_w) % p.tiles_h;
         const int tb = m_blk / (p.tiles_w * p.tiles_h);
         const int ww = r % p.BW, hh = (r / p.BW) % p.BH, bb = r / (p.BW * p.BH);
         const int w = tw * p.BW + ww, h = th * p.BH + hh, b = tb * p.BB + bb;
-        valid = (w < p.W) && (h < p.H) && (b < p.NB);
-        token = ((long long)b * p.H + h) * p.W + w;
+        valid_own = (w < p.W) && (h < p.H) && (b < p.NB);
+        token_own = (b * p.H + h) * p.W + w;
       }
-      const int rv_row = p.rowvec ? (int)((token / p.rv_div) % p.rv_mod) : 0;
+      const float* rv_ptr = p.rowvec ? p.rowvec + (long long)((token_own / p.rv_div) % p.rv_mod) * p.ld_rowvec : nullptr;
+      const int n_out_base = n_blk * tile_out_cols;
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256;
-      if (p.act != 2) {
-        for (int c0 = 0; c0 < p.TN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);
-          tmem_ld_wait();
-          const int n0 = n_blk * p.TN + c0;
+      for (int c0 = 0; c0 < tile_out_cols; c0 += 64) {
+        const int gw = min(64, tile_out_cols - c0);
+        // ---------------- phase A
+        for (int sub = 0; sub < gw; sub += 32) {
+          float f[32];
+          if (p.act != 2) {
+            uint32_t v[32];
+            tmem_ld32(t_row + c0 + sub, v);
+            tmem_ld_wait();
+            const int n0 = n_out_base + c0 + sub;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
+            for (int g = 0; g < 8; ++g) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
+              const bool in = n0 + g * 4 + 4 <= p.N;
+              if (p.bias && in) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
+              if (rv_ptr && in) rv = __ldg(reinterpret_cast<const float4*>(rv_ptr + n0 + g * 4));
+              f[g * 4 + 0] = (__uint_as_float(v[g * 4 + 0]) + bv.x) * p.s_acc + rv.x;
+              f[g * 4 + 1] = (__uint_as_float(v[g * 4 + 1]) + bv.y) * p.s_acc + rv.y;
+              f[g * 4 + 2] = (__uint_as_float(v[g * 4 + 2]) + bv.z) * p.s_acc + rv.z;
+              f[g * 4 + 3] = (__uint_as_float(v[g * 4 + 3]) + bv.w) * p.s_acc + rv.w;
+            }
+            if (p.act == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-            const int n = n0 + g * 8;
-            finish8(p, f, token, n, n, rv_row, valid && (n + 8 <= p.N));
+              for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
+            }
+          } else {
+            uint32_t va[32], vg[32];
+            tmem_ld32(t_row + c0 + sub, va);
+            tmem_ld32(t_row + half + c0 + sub, vg);
+            tmem_ld_wait();
+            const int nb = n_blk * p.TN + c0 + sub;  // bias index of the value columns (gate: + half)
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) {
+                ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
+                bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + half + g * 4));
+              }
+              f[g * 4 + 0] = (__uint_as_float(va[g * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 0]) + bg.x);
+              f[g * 4 + 1] = (__uint_as_float(va[g * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 1]) + bg.y);
+              f[g * 4 + 2] = (__uint_as_float(va[g * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 2]) + bg.z);
+              f[g * 4 + 3] = (__uint_as_float(va[g * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 3]) + bg.w);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int ch = (sub >> 2) + j;
+            const int slot = (ch & 8) | ((ch ^ lane) & 7);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 256 + slot * 16), "f"(f[j * 4]),
+                         "f"(f[j * 4 + 1]), "f"(f[j * 4 + 2]), "f"(f[j * 4 + 3])
+                         : "memory");
           }
         }
-      } else {
-        const int half = p.TN >> 1;
-        for (int c0 = 0; c0 < half; c0 += 32) {
-          uint32_t va[32], vg[32];
-          tmem_ld32(t_row + c0, va);
-          tmem_ld32(t_row + half + c0, vg);
-          tmem_ld_wait();
-          const int nb0 = n_blk * p.TN + c0;      // bias index of the value columns
-          const int no0 = n_blk * half + c0;      // output column
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int nb = nb0 + g * 8, no = no0 + g * 8;
-            const bool ok = valid && (nb + half + 8 <= p.N);
-            float f[8];
-            if (ok) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float a = __uint_as_float(va[g * 8 + i]), gt = __uint_as_float(vg[g * 8 + i]);
-                if (p.bias) {
-                  a += __ldg(p.bias + nb + i);
-                  gt += __ldg(p.bias + nb + half + i);
-                }
-                f[i] = a * gelu_erf_f(gt);
+        __syncwarp();
+        // ---------------- phase B
+        const int cpr = gw >> 2;             // 16-byte fp32 chunks per row: 16 or 8
+        const int rows_per_it = 32 / cpr;    // 2 or 4
+        const int ch = lane % cpr;
+        const int n = n_out_base + c0 + ch * 4;
+        const bool n_ok = n + 4 <= n_out_total;
+        for (int it = 0; it < 32; it += rows_per_it) {
+          const int row = it + lane / cpr;
+          const int slot = (ch & 8) | ((ch ^ row) & 7);
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(stg + row * 256 + slot * 16));
+          const int tok = __shfl_sync(0xffffffffu, token_own, row);
+          const int ok = __shfl_sync(0xffffffffu, valid_own, row);
+          if (ok && n_ok) {
+            if (p.res1) {
+              const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.res1) +
+                                                                   (long long)tok * p.ld_res1 + n));
+              float2 a, b;
+              if (p.bf16) {
+                a = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u));
+                b = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+              } else {
+                a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
               }
-              uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + token * p.ldo + no;
-              *reinterpret_cast<uint4*>(op) = pack8(f, p.bf16);
+              v.x += p.s_res1 * a.x; v.y += p.s_res1 * a.y; v.z += p.s_res1 * b.x; v.w += p.s_res1 * b.y;
+            }
+            if (p.res2) {
+              const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.res2) +
+                                                                   (long long)tok * p.ld_res2 + n));
+              float2 a, b;
+              if (p.bf16) {
+                a = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u));
+                b = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+              } else {
+                a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+              }
+              v.x += p.s_res2 * a.x; v.y += p.s_res2 * a.y; v.z += p.s_res2 * b.x; v.w += p.s_res2 * b.y;
+            }
+            if (p.out_f32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)tok * p.ldo + n) = v;
+            } else {
+              uint2 o;
+              if (p.bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                o.x = *reinterpret_cast<uint32_t*>(&lo);
+                o.y = *reinterpret_cast<uint32_t*>(&hi);
+              } else {
+                __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+                o.x = *reinterpret_cast<uint32_t*>(&lo);
+                o.y = *reinterpret_cast<uint32_t*>(&hi);
+              }
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)tok * p.ldo + n) = o;
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
@@ -334,7 +366,7 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   CUtensorMap tmA, tmB;
   if (d->a_mode == 0) {
     VB_REQUIRE(d->ntaps == 1, "b200v_gemm: linear mode takes one tap");
-    VB_REQUIRE(d->tokens > 0 && d->tokens < (1ll << 31), "b200v_gemm: tokens out of range");
+    VB_REQUIRE(d->tokens > 0 && d->tokens < (1ll << 31) - 256, "b200v_gemm: tokens out of range");
     p.W = (int)d->tokens; p.H = 1; p.NB = 1;
     p.BW = 128; p.BH = 1; p.BB = 1;
     p.tiles_w = (int)((d->tokens + 127) / 128); p.tiles_h = 1;
@@ -345,8 +377,9 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     uint32_t es[2] = {1, 1};
     if (encode_tmap_16bit(&tmA, d->a, 2, dims, strides, box, es, d->bf16)) return 3;
   } else {
-    VB_REQUIRE(d->W > 0 && d->H > 0 && d->NB > 0 && (long long)d->W * d->H * d->NB == d->tokens,
-               "b200v_gemm: W*H*NB != tokens");
+    VB_REQUIRE(d->W > 0 && d->H > 0 && d->NB > 0 && (long long)d->W * d->H * d->NB == d->tokens &&
+                   d->tokens < (1ll << 31) - 256,
+               "b200v_gemm: W*H*NB != tokens (or >= 2^31)");
     VB_REQUIRE(d->box_w > 0 && d->box_h > 0 && d->box_b > 0 && d->box_w * d->box_h * d->box_b == 128,
                "b200v_gemm: box_w*box_h*box_b must be 128");
     p.W = d->W; p.H = d->H; p.NB = d->NB;
@@ -379,7 +412,8 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   p.n_tiles = (d->N + d->tile_n - 1) / d->tile_n;
   p.bf16 = d->bf16;
   p.stage_bytes = kABytes + ((d->tile_n * 128 + 1023) / 1024) * 1024;
-  p.nstages = 200 * 1024 / p.stage_bytes;
+  constexpr int kStagingBytes = 4 * 32 * 256;  // epilogue transpose buffers (4 warps x 32 rows x 64 fp32)
+  p.nstages = (227 * 1024 - 2048 - kStagingBytes) / p.stage_bytes;
   if (p.nstages > kMaxStages) p.nstages = kMaxStages;
   p.out = d->out; p.ldo = d->ldo; p.out_f32 = d->out_f32; p.act = d->act;
   p.bias = d->bias;
@@ -389,7 +423,7 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   p.res2 = d->res2; p.ld_res2 = d->ld_res2; p.s_res2 = d->s_res2;
   p.s_acc = d->s_acc;
 
-  const int smem_bytes = 1024 + 1024 + p.nstages * p.stage_bytes;
+  const int smem_bytes = 1024 + 1024 + p.nstages * p.stage_bytes + kStagingBytes;
   static bool attr_set = false;
   if (!attr_set) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -166,10 +166,11 @@ gn_apply_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// LayerNorm: one warp per token, values kept in registers (C <= 2560), two-pass statistics.
+// LayerNorm: one warp per token, the row lives in registers (NV 16-byte vectors per lane), two-pass
+// statistics.  Templated on NV so that the common widths (C = 320: NV 2, 640: 3, 1280: 5) keep the
+// register count low and the SM full of warps (the kernel is a pure HBM stream).
 // ------------------------------------------------------------------------------------------
-constexpr int kLnMaxV = 10;  // vectors of 8 per lane
-
+template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, long long tokens,
                  int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -178,17 +179,25 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict
   const long long token = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (token >= tokens) return;
   const int nvec = C >> 3;
-  float v[kLnMaxV][8];
+  uint4 raw[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) raw[j] = __ldg(reinterpret_cast<const uint4*>(x + token * ldx + vi * 8));
+  }
+  float v[NV][8];
   const float* av = addvec ? addvec + ((token / av_div) % av_mod) * ld_addvec : nullptr;
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < kLnMaxV; ++j) {
+  for (int j = 0; j < NV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
-      h8_to_f(__ldg(reinterpret_cast<const uint4*>(x + token * ldx + vi * 8)), v[j]);
+      h8_to_f(raw[j], v[j]);
       if (av) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[j][i] += __ldg(av + vi * 8 + i);
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8 + 4));
+        v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
+        v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) sum += v[j][i];
@@ -197,7 +206,7 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict
   const float mean = warp_sum(sum) / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int j = 0; j < kLnMaxV; ++j) {
+  for (int j = 0; j < NV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
 #pragma unroll
@@ -209,12 +218,18 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
 #pragma unroll
-  for (int j = 0; j < kLnMaxV; ++j) {
+  for (int j = 0; j < NV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * __ldg(gamma + vi * 8 + i) + __ldg(beta + vi * 8 + i);
+      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * gg[i] + bb[i];
       *reinterpret_cast<uint4*>(y + token * ldy + vi * 8) = f_to_h8(o);
     }
   }
@@ -505,7 +520,8 @@ __global__ void sampler_prepare_kernel(float* __restrict__ x, const float* __res
 __global__ void sampler_update_kernel(float* __restrict__ x, const float* __restrict__ net,
                                       const float* __restrict__ cond_frame, const float* __restrict__ mask,
                                       const float* __restrict__ scales, const float* __restrict__ sigmas,
-                                      const int* __restrict__ step_idx, int num_steps, int T, int h, int w) {
+                                      const int* __restrict__ step_idx, int num_steps, int T, int h, int w,
+                                      long long ld_net) {
   const int step = *step_idx;
   const float sigma = sigmas[step], sigma_next = sigmas[step + 1];
   const float c_skip = 1.0f / (sigma * sigma + 1.0f);
@@ -515,8 +531,8 @@ __global__ void sampler_update_kernel(float* __restrict__ x, const float* __rest
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int t = (int)(i / hw), pix = (int)(i % hw);
-  const float4 nu = *reinterpret_cast<const float4*>(net + ((long long)t * hw + pix) * 4);
-  const float4 nc = *reinterpret_cast<const float4*>(net + (((long long)T + t) * hw + pix) * 4);
+  const float4 nu = *reinterpret_cast<const float4*>(net + ((long long)t * hw + pix) * ld_net);
+  const float4 nc = *reinterpret_cast<const float4*>(net + (((long long)T + t) * hw + pix) * ld_net);
   const float un[4] = {nu.x, nu.y, nu.z, nu.w}, cn[4] = {nc.x, nc.y, nc.z, nc.w};
   const float sc = scales[t];
   const bool final_step = (step + 1 == num_steps);
@@ -628,12 +644,21 @@ extern "C" int b200v_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy,
                                const float* gamma, const float* beta, float eps, const float* addvec,
                                int64_t ld_addvec, int32_t av_div, int32_t av_mod, void* stream) {
   VB_REQUIRE(x && y && gamma && beta, "layernorm: null pointer");
-  VB_REQUIRE(C % 8 == 0 && C <= kLnMaxV * 256 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm: C=%d unsupported", C);
-  VB_REQUIRE(!addvec || (av_div > 0 && av_mod > 0), "layernorm: bad addvec args");
+  VB_REQUIRE(C % 8 == 0 && C <= 2560 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm: C=%d unsupported", C);
+  VB_REQUIRE(!addvec || (av_div > 0 && av_mod > 0 && ld_addvec % 4 == 0), "layernorm: bad addvec args");
   const int wpb = 8;
-  layernorm_kernel<<<(unsigned)((tokens + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, (__half*)y, ldy, tokens, C, gamma, beta, eps, addvec, ld_addvec, av_div > 0 ? av_div : 1,
-      av_mod > 0 ? av_mod : 1);
+  const unsigned grid = (unsigned)((tokens + wpb - 1) / wpb);
+  const int nv = (C / 8 + 31) / 32;
+  const int ad = av_div > 0 ? av_div : 1, am = av_mod > 0 ? av_mod : 1;
+#define VB_LN_LAUNCH(NV)                                                                                             \
+  layernorm_kernel<NV><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, tokens, C, \
+                                                                     gamma, beta, eps, addvec, ld_addvec, ad, am)
+  if (nv <= 1) VB_LN_LAUNCH(1);
+  else if (nv <= 2) VB_LN_LAUNCH(2);
+  else if (nv <= 3) VB_LN_LAUNCH(3);
+  else if (nv <= 5) VB_LN_LAUNCH(5);
+  else VB_LN_LAUNCH(10);
+#undef VB_LN_LAUNCH
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -726,13 +751,14 @@ extern "C" int b200v_sampler_prepare(float* x, const float* cond_frame, const fl
   return 0;
 }
 
-extern "C" int b200v_sampler_update(float* x, const float* net_out, const float* cond_frame, const float* mask,
-                                    const float* scales, const float* sigmas, int32_t* step_idx, int32_t num_steps,
-                                    int32_t T, int32_t h, int32_t w, void* stream) {
+extern "C" int b200v_sampler_update(float* x, const float* net_out, int64_t ld_net, const float* cond_frame,
+                                    const float* mask, const float* scales, const float* sigmas, int32_t* step_idx,
+                                    int32_t num_steps, int32_t T, int32_t h, int32_t w, void* stream) {
   VB_REQUIRE(x && net_out && scales && sigmas && step_idx, "sampler_update: null pointer");
+  VB_REQUIRE(ld_net >= 4 && ld_net % 4 == 0, "sampler_update: ld_net must be a multiple of 4");
   const long long total = (long long)T * h * w;
   sampler_update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_steps, T, h, w);
+      x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_steps, T, h, w, ld_net);
   step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_idx);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -807,7 +833,7 @@ softmax_rows_kernel(const float* __restrict__ x, long long ld_in, __half* __rest
 // already holds.  x: token-major fp32 [T*HW, C]; out: NCHW fp32 frames starting at out_frame0.
 __global__ void time_mix_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                       const float* __restrict__ bias, float* __restrict__ out, const int* __restrict__ blend,
-                                      int T, int HW, int C, int out_frame0, int skip_frames) {
+                                      int T, int HW, int C, int out_frame0, int skip_frames, long long ldx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)T * HW) return;
   const int t = (int)(i / HW), pix = (int)(i % HW);
@@ -817,7 +843,7 @@ __global__ void time_mix_small_kernel(const float* __restrict__ x, const float* 
   for (int kt = 0; kt < 3; ++kt) {
     const int tt = t + kt - 1;
     if (tt < 0 || tt >= T) continue;
-    const float* xp = x + ((long long)tt * HW + pix) * C;
+    const float* xp = x + ((long long)tt * HW + pix) * ldx;
     for (int ci = 0; ci < C; ++ci) {
       const float xv = xp[ci];
       for (int co = 0; co < C; ++co) acc[co] = fmaf(xv, w[(co * C + ci) * 3 + kt], acc[co]);
@@ -840,13 +866,13 @@ extern "C" int b200v_softmax_rows(const float* x, int64_t ld_in, void* y_f16, in
   return 0;
 }
 
-extern "C" int b200v_time_mix_small(const float* x, const float* w, const float* bias, float* out, const int32_t* blend,
-                                    int32_t T, int32_t HW, int32_t C, int32_t out_frame0, int32_t skip_frames,
-                                    void* stream) {
+extern "C" int b200v_time_mix_small(const float* x, int64_t ldx, const float* w, const float* bias, float* out,
+                                    const int32_t* blend, int32_t T, int32_t HW, int32_t C, int32_t out_frame0,
+                                    int32_t skip_frames, void* stream) {
   VB_REQUIRE(x && w && out && C >= 1 && C <= 4, "time_mix_small: bad args");
   const long long total = (long long)T * HW;
   vb::time_mix_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, w, bias, out, blend, T, HW, C, out_frame0, skip_frames);
+      x, w, bias, out, blend, T, HW, C, out_frame0, skip_frames, ldx);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -318,7 +318,7 @@ def sampler_prepare(x, cond_frame, mask, concat_u, concat_c, sigmas, step_idx, u
 def sampler_update(x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_steps, T, h, w):
     _count(2)
     _prof_begin("other", "sampler_update", 0.0, 0.0)
-    _lib.check(_lib.load().b200v_sampler_update(x.data_ptr(), net_out.data_ptr(), _ptr(cond_frame), _ptr(mask),
+    _lib.check(_lib.load().b200v_sampler_update(x.data_ptr(), net_out.data_ptr(), net_out.stride(0), _ptr(cond_frame), _ptr(mask),
                                                 scales.data_ptr(), sigmas.data_ptr(), step_idx.data_ptr(), num_steps,
                                                 T, h, w, _stream()), "b200v_sampler_update")
     _prof_end()
@@ -355,7 +355,7 @@ def softmax_rows(x, y):
 def time_mix_small(x, w, bias, out, blend, T, HW, Cc, out_frame0=0, skip_frames=0):
     _count(1)
     _prof_begin("other", "time_mix_small", 0.0, 0.0)
-    _lib.check(_lib.load().b200v_time_mix_small(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(blend),
+    _lib.check(_lib.load().b200v_time_mix_small(x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(blend),
                                                 T, HW, Cc, out_frame0, skip_frames, _stream()), "b200v_time_mix_small")
     _prof_end()
     return out

@@ -130,7 +130,15 @@ class UNetRuntime:
         self.out_norm = self._norm("out.0")
         self.out_gn_idx = self.n_gn
         self.n_gn += 1
-        self.out_w, self.out_b = self._f32("out.2.weight"), self._f32("out.2.bias")
+        # out[2]: conv3x3 320 -> 4 as a tap-GEMM with N padded to 8 (fp32 output, 4 channels used)
+        ow = conv_weight_to_taps(self._f32("out.2.weight"))
+        oc = ow.shape[0]
+        assert oc <= 8
+        w8 = torch.zeros(8, ow.shape[1], dtype=torch.float16, device=self.dev)
+        w8[:oc] = ow.to(torch.float16)
+        b8 = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        b8[:oc] = self._f32("out.2.bias")
+        self.out_conv = Lin(w8.contiguous(), b8, 32)
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name: str, rows: int, cols: int, dtype=torch.float16) -> torch.Tensor:
@@ -265,7 +273,8 @@ class UNetRuntime:
     # ------------------------------------------------------------------ forward
     def forward(self, x_tokens: torch.Tensor, c_noise: torch.Tensor, cond_mask: Optional[torch.Tensor],
                 h: int, w: int, net_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x_tokens: [(B h w), 8] fp16 (x*c_in | concat); c_noise: [B] fp32; returns [(B h w), out_ch] fp32."""
+        """x_tokens: [(B h w), 8] fp16 (x*c_in | concat); c_noise: [B] fp32; returns [(B h w), 8] fp32 whose
+        first out_channels columns are the network output."""
         assert self.cond is not None, "call set_conditioning() first"
         cfg, T = self.cfg, self.T
         B = c_noise.numel()
@@ -348,8 +357,8 @@ class UNetRuntime:
         M = B * h * w
         a = self._gn(cur, self.buf("out.a", M, mc), B, h * w, self.out_norm, 1e-5, True, self.out_gn_idx)
         if net_out is None:
-            net_out = self.buf("unet.out", M, cfg.out_channels, torch.float32)
-        ops.conv3x3_small_cout(a, self.out_w, self.out_b, net_out, B, h, w)
+            net_out = self.buf("unet.out", M, 8, torch.float32)
+        self.gemm(a, self.out_conv, net_out, taps=ops.TAPS_3X3, geom=(w, h, B))
         return net_out
 
     def _mlp_step(self, temb, mlp, name):

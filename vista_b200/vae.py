@@ -80,7 +80,12 @@ class DecoderRuntime:
         self.norm_out = self._norm("norm_out")
         self.norm_out_idx = self.n_gn
         self.n_gn += 1
-        self.out_w, self.out_b = self._f32("conv_out.weight"), self._f32("conv_out.bias")
+        ow = conv_weight_to_taps(self._f32("conv_out.weight"))
+        w8 = torch.zeros(8, ow.shape[1], dtype=torch.float16, device=self.dev)
+        w8[: ow.shape[0]] = ow.to(torch.float16)
+        b8 = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        b8[: ow.shape[0]] = self._f32("conv_out.bias")
+        self.out_conv = Lin(w8.contiguous(), b8, 32)
         self.tmix_w = self._f32("conv_out.time_mix_conv.weight").reshape(self.cfg.out_ch, self.cfg.out_ch, 3).contiguous()
         self.tmix_b = self._f32("conv_out.time_mix_conv.bias")
 
@@ -165,7 +170,7 @@ class DecoderRuntime:
         M = T * h * w
         a = ops.groupnorm(x, self.buf("d.a1", M, self.plan.final_ch), T, h * w, self.norm_out[0], self.norm_out[1], 1e-6,
                           True, self.gn_stats[self.norm_out_idx, :T], groups=cfg.num_groups, ws=self.gn_ws)
-        y = ops.conv3x3_small_cout(a, self.out_w, self.out_b, self.buf("d.y", M, cfg.out_ch, torch.float32), T, h, w)
+        y = self.gemm(a, self.out_conv, self.buf("d.y", M, 8, torch.float32), taps=ops.TAPS_3X3, geom=(w, h, T))
         ops.time_mix_small(y, self.tmix_w, self.tmix_b, out, blend, T, h * w, cfg.out_ch, out_frame0, skip_frames)
         return out
 
