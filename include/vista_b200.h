@@ -87,6 +87,11 @@ int b200v_gemm(const b200v_gemm_desc* d, void* stream);
 int b200v_attention_spatial(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                             void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
+/* Same contract, second-generation kernel: two 128-query tiles per CTA in ping-pong (two softmax
+ * warpgroups), output accumulator and row sum kept in TMEM (ones-column trick), lazy rescaling. */
+int b200v_attention_spatial_v2(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                               void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
+
 /* Temporal self-attention over the T frames of each pixel (seq len T <= 32, head dim 64).
  * Replaces the batchified xformers call at vwm/modules/attention.py:384-399 reached from
  * vwm/modules/video_attention.py:127 and both "(b t) s c <-> (b s) t c" rearranges (:116,:140):

@@ -141,28 +141,47 @@ def test_gemm_temporal_conv(ops, nb, T, S, Cc):
 
 
 # ------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("frames,seq,heads", [(2, 128, 1), (3, 144, 2), (2, 576, 4), (1, 2304, 2), (2, 200, 1)])
-def test_attention_spatial(ops, frames, seq, heads):
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("frames,seq,heads", [(2, 128, 1), (3, 144, 2), (2, 576, 4), (1, 2304, 2), (2, 200, 1), (1, 256, 1),
+                                              (2, 300, 1)])
+def test_attention_spatial(ops, frames, seq, heads, impl):
     Cc = heads * 64
     qkv = rnd(frames * seq, 3 * Cc, seed=23)
     out = torch.zeros(frames * seq, Cc, dtype=torch.float16, device=dev())
-    ops.attention_spatial(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], out, frames, seq, heads)
+    ops.attention_spatial(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], out, frames, seq, heads, impl=impl)
     torch.cuda.synchronize()
     q, k, v = (t.float().reshape(frames, seq, heads, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
     ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(frames * seq, Cc)
     check(out, ref, rtol=4e-3, atol=2e-3, name="attn spatial")
 
 
-def test_attention_spatial_peaky(ops):
-    """Large logits: the running max / rescale path must hold (scores ~ +-40)."""
-    frames, seq, heads = 1, 384, 1
+@pytest.mark.parametrize("impl", [1, 2])
+def test_attention_spatial_peaky(ops, impl):
+    """Large logits: the running max / (lazy) rescale path must hold (scores ~ +-40)."""
+    frames, seq, heads = 1, 640, 1
     qkv = rnd(frames * seq, 192, seed=24, scale=2.5)
     out = torch.zeros(frames * seq, 64, dtype=torch.float16, device=dev())
-    ops.attention_spatial(qkv[:, :64], qkv[:, 64:128], qkv[:, 128:], out, frames, seq, heads)
+    ops.attention_spatial(qkv[:, :64], qkv[:, 64:128], qkv[:, 128:], out, frames, seq, heads, impl=impl)
     torch.cuda.synchronize()
     q, k, v = (t.float().reshape(1, seq, 1, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
     ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(seq, 64)
     check(out, ref, rtol=1e-2, atol=1e-2, name="attn peaky")
+
+
+def test_attention_spatial_increasing_max(ops):
+    """Keys ordered so that the row maximum keeps growing block after block: exercises every lazy-rescale branch."""
+    seq = 1024
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(seq, 64, generator=g)
+    k = torch.randn(seq, 64, generator=g) * torch.linspace(0.2, 6.0, seq)[:, None]
+    v = torch.randn(seq, 64, generator=g)
+    qkv = torch.cat([q, k, v], 1).half().to(dev())
+    out = torch.zeros(seq, 64, dtype=torch.float16, device=dev())
+    ops.attention_spatial(qkv[:, :64], qkv[:, 64:128], qkv[:, 128:], out, 1, seq, 1, impl=2)
+    torch.cuda.synchronize()
+    qq, kk, vv = (t.float().reshape(1, seq, 1, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
+    ref = F.scaled_dot_product_attention(qq, kk, vv).permute(0, 2, 1, 3).reshape(seq, 64)
+    check(out, ref, rtol=1e-2, atol=1e-2, name="attn increasing max")
 
 
 @pytest.mark.parametrize("nb,T,S,heads", [(2, 25, 32, 1), (2, 25, 20, 5), (1, 14, 16, 2), (2, 25, 8, 20)])

@@ -1,7 +1,8 @@
 // Tap-GEMM: persistent, warp-specialised tcgen05 kernel.
-//   warp 4 : TMA producer  (A tile 128 tokens x 64 ch per tap / K-chunk, B tile tile_n x 64)
-//   warp 5 : TMEM owner + single-thread tcgen05.mma issuer (M=128, N=tile_n, K=16 per instruction)
-//   warps 0-3 : epilogue (tcgen05.ld -> fused bias / row-vector / activation / residuals -> global)
+//   warp 8 : TMA producer  (A tile 128 tokens x 64 ch per tap / K-chunk, B tile tile_n x 64)
+//   warp 9 : TMEM owner + single-thread tcgen05.mma issuer (M=128, N=tile_n, K=16 per instruction)
+//   warps 0-7 : epilogue, two per TMEM lane quadrant (tcgen05.ld -> fused bias / row-vector / activation /
+//               GEGLU -> smem transpose -> coalesced residual loads and stores)
 // Two accumulator stages in TMEM (2 x 256 columns) let the epilogue of tile i overlap the MMAs of
 // tile i+1.  The 3x3 / (3,1,1) convolutions are implicit GEMMs: the A tile of every tap is a
 // shifted 4-D TMA box of the token-major activation, zero padding comes from TMA OOB fill.
@@ -72,7 +73,70 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf16) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ float2 unpack2(uint32_t w, int bf16) {
+  if (bf16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
+  if (bf16) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// Phase B of the epilogue: the warp walks its 32 staged rows (32 fp32 columns = 8 chunks of 16 bytes per row,
+// 4 rows per instruction) so that every residual load / output store covers a contiguous 64-byte (fp16) or
+// 128-byte (fp32) row segment.  All 8 iterations are batched: loads are issued before the first use.
+__device__ __forceinline__ void epilogue_phase_b(const TGParams& p, uint32_t stg, int lane, int token_own, int valid_own,
+                                                 int n_base, int n_out_total) {
+  const int ch = lane & 7;
+  const int rsub = lane >> 3;
+  const int n = n_base + ch * 4;
+  const bool n_ok = n + 4 <= n_out_total;
+  const uint16_t* r1p = reinterpret_cast<const uint16_t*>(p.res1);
+  const uint16_t* r2p = reinterpret_cast<const uint16_t*>(p.res2);
+  float4 v[8];
+  uint2 u1[8], u2[8];
+  int tok[8];
+  bool ok[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + rsub;
+    const int slot = (ch ^ row) & 7;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                 : "r"(stg + row * 128 + slot * 16));
+    tok[i] = __shfl_sync(0xffffffffu, token_own, row);
+    ok[i] = (__shfl_sync(0xffffffffu, valid_own, row) != 0) && n_ok;
+    u1[i] = make_uint2(0, 0);
+    u2[i] = make_uint2(0, 0);
+    if (r1p && ok[i]) u1[i] = __ldg(reinterpret_cast<const uint2*>(r1p + (long long)tok[i] * p.ld_res1 + n));
+    if (r2p && ok[i]) u2[i] = __ldg(reinterpret_cast<const uint2*>(r2p + (long long)tok[i] * p.ld_res2 + n));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (!ok[i]) continue;
+    float4 o = v[i];
+    if (r1p) {
+      const float2 a = unpack2(u1[i].x, p.bf16), b = unpack2(u1[i].y, p.bf16);
+      o.x += p.s_res1 * a.x; o.y += p.s_res1 * a.y; o.z += p.s_res1 * b.x; o.w += p.s_res1 * b.y;
+    }
+    if (r2p) {
+      const float2 a = unpack2(u2[i].x, p.bf16), b = unpack2(u2[i].y, p.bf16);
+      o.x += p.s_res2 * a.x; o.y += p.s_res2 * a.y; o.z += p.s_res2 * b.x; o.w += p.s_res2 * b.y;
+    }
+    if (p.out_f32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)tok[i] * p.ldo + n) = o;
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)tok[i] * p.ldo + n) =
+          make_uint2(pack2(o.x, o.y, p.bf16), pack2(o.z, o.w, p.bf16));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(320, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -95,21 +159,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 256);
     }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -140,7 +204,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       int stage = 0;
@@ -175,15 +239,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0..3)
-    // Phase A: thread = tile row (TMEM lane): accumulator -> (+bias)*s_acc + rowvec -> act / GEGLU, fp32,
-    //          written to a per-warp staging buffer (32 rows x 64 cols, 16-byte chunks XOR-swizzled by row).
-    // Phase B: the warp re-reads the buffer row-segment-wise so that residual loads and output stores are
-    //          128-byte contiguous per row (coalesced) instead of one 16-byte piece per row and instruction.
+    // ------------------------------------------------------------ epilogue (warps 0..7)
+    // Warp w owns TMEM lane quadrant w % 4 (rows 32*(w%4) ..) and every second 32-column group (w / 4).
+    // Phase A: thread = tile row: accumulator -> (+bias)*s_acc + rowvec -> act / GEGLU, fp32, written to the
+    //          warp's staging buffer (32 rows x 32 cols, 16-byte chunks XOR-swizzled by row).
+    // Phase B: coalesced residual loads / output stores (epilogue_phase_b).
     int as = 0;
     uint32_t aphase = 0;
-    const int r = warp * 32 + lane;  // row of the tile == TMEM lane
-    const uint32_t stg = smem_u32(stages + p.nstages * p.stage_bytes) + warp * (32 * 256);
+    const int quad = warp & 3, wg = warp >> 2;
+    const int r = quad * 32 + lane;  // row of the tile == TMEM lane
+    const uint32_t stg = smem_u32(stages + p.nstages * p.stage_bytes) + warp * (32 * 128);
     const int half = p.TN >> 1;
     const int tile_out_cols = (p.act == 2) ? half : p.TN;
     const int n_out_total = (p.act == 2) ? (p.N >> 1) : p.N;
@@ -206,120 +271,59 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_out_base = n_blk * tile_out_cols;
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256;
-      for (int c0 = 0; c0 < tile_out_cols; c0 += 64) {
-        const int gw = min(64, tile_out_cols - c0);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
+      for (int c0 = wg * 32; c0 < tile_out_cols; c0 += 64) {
         // ---------------- phase A
-        for (int sub = 0; sub < gw; sub += 32) {
-          float f[32];
-          if (p.act != 2) {
-            uint32_t v[32];
-            tmem_ld32(t_row + c0 + sub, v);
-            tmem_ld_wait();
-            const int n0 = n_out_base + c0 + sub;
+        float f[32];
+        if (p.act != 2) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c0, v);
+          tmem_ld_wait();
+          const int n0 = n_out_base + c0;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
-              const bool in = n0 + g * 4 + 4 <= p.N;
-              if (p.bias && in) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
-              if (rv_ptr && in) rv = __ldg(reinterpret_cast<const float4*>(rv_ptr + n0 + g * 4));
-              f[g * 4 + 0] = (__uint_as_float(v[g * 4 + 0]) + bv.x) * p.s_acc + rv.x;
-              f[g * 4 + 1] = (__uint_as_float(v[g * 4 + 1]) + bv.y) * p.s_acc + rv.y;
-              f[g * 4 + 2] = (__uint_as_float(v[g * 4 + 2]) + bv.z) * p.s_acc + rv.z;
-              f[g * 4 + 3] = (__uint_as_float(v[g * 4 + 3]) + bv.w) * p.s_acc + rv.w;
-            }
-            if (p.act == 1) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
-            }
-          } else {
-            uint32_t va[32], vg[32];
-            tmem_ld32(t_row + c0 + sub, va);
-            tmem_ld32(t_row + half + c0 + sub, vg);
-            tmem_ld_wait();
-            const int nb = n_blk * p.TN + c0 + sub;  // bias index of the value columns (gate: + half)
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) {
-                ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
-                bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + half + g * 4));
-              }
-              f[g * 4 + 0] = (__uint_as_float(va[g * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 0]) + bg.x);
-              f[g * 4 + 1] = (__uint_as_float(va[g * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 1]) + bg.y);
-              f[g * 4 + 2] = (__uint_as_float(va[g * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 2]) + bg.z);
-              f[g * 4 + 3] = (__uint_as_float(va[g * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 3]) + bg.w);
-            }
+          for (int g = 0; g < 8; ++g) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool in = n0 + g * 4 + 4 <= p.N;
+            if (p.bias && in) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
+            if (rv_ptr && in) rv = __ldg(reinterpret_cast<const float4*>(rv_ptr + n0 + g * 4));
+            f[g * 4 + 0] = (__uint_as_float(v[g * 4 + 0]) + bv.x) * p.s_acc + rv.x;
+            f[g * 4 + 1] = (__uint_as_float(v[g * 4 + 1]) + bv.y) * p.s_acc + rv.y;
+            f[g * 4 + 2] = (__uint_as_float(v[g * 4 + 2]) + bv.z) * p.s_acc + rv.z;
+            f[g * 4 + 3] = (__uint_as_float(v[g * 4 + 3]) + bv.w) * p.s_acc + rv.w;
           }
+          if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int ch = (sub >> 2) + j;
-            const int slot = (ch & 8) | ((ch ^ lane) & 7);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 256 + slot * 16), "f"(f[j * 4]),
-                         "f"(f[j * 4 + 1]), "f"(f[j * 4 + 2]), "f"(f[j * 4 + 3])
-                         : "memory");
+            for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
           }
+        } else {
+          uint32_t va[32], vg[32];
+          tmem_ld32(t_row + c0, va);
+          tmem_ld32(t_row + half + c0, vg);
+          tmem_ld_wait();
+          const int nb = n_blk * p.TN + c0;  // bias index of the value columns (gate: + half)
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) {
+              ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + half + g * 4));
+            }
+            f[g * 4 + 0] = (__uint_as_float(va[g * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 0]) + bg.x);
+            f[g * 4 + 1] = (__uint_as_float(va[g * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 1]) + bg.y);
+            f[g * 4 + 2] = (__uint_as_float(va[g * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 2]) + bg.z);
+            f[g * 4 + 3] = (__uint_as_float(va[g * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 3]) + bg.w);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int slot = (j ^ lane) & 7;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + slot * 16), "f"(f[j * 4]),
+                       "f"(f[j * 4 + 1]), "f"(f[j * 4 + 2]), "f"(f[j * 4 + 3])
+                       : "memory");
         }
         __syncwarp();
         // ---------------- phase B
-        const int cpr = gw >> 2;             // 16-byte fp32 chunks per row: 16 or 8
-        const int rows_per_it = 32 / cpr;    // 2 or 4
-        const int ch = lane % cpr;
-        const int n = n_out_base + c0 + ch * 4;
-        const bool n_ok = n + 4 <= n_out_total;
-        for (int it = 0; it < 32; it += rows_per_it) {
-          const int row = it + lane / cpr;
-          const int slot = (ch & 8) | ((ch ^ row) & 7);
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(stg + row * 256 + slot * 16));
-          const int tok = __shfl_sync(0xffffffffu, token_own, row);
-          const int ok = __shfl_sync(0xffffffffu, valid_own, row);
-          if (ok && n_ok) {
-            if (p.res1) {
-              const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.res1) +
-                                                                   (long long)tok * p.ld_res1 + n));
-              float2 a, b;
-              if (p.bf16) {
-                a = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u));
-                b = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
-              } else {
-                a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-                b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-              }
-              v.x += p.s_res1 * a.x; v.y += p.s_res1 * a.y; v.z += p.s_res1 * b.x; v.w += p.s_res1 * b.y;
-            }
-            if (p.res2) {
-              const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.res2) +
-                                                                   (long long)tok * p.ld_res2 + n));
-              float2 a, b;
-              if (p.bf16) {
-                a = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u));
-                b = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
-              } else {
-                a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-                b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-              }
-              v.x += p.s_res2 * a.x; v.y += p.s_res2 * a.y; v.z += p.s_res2 * b.x; v.w += p.s_res2 * b.y;
-            }
-            if (p.out_f32) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)tok * p.ldo + n) = v;
-            } else {
-              uint2 o;
-              if (p.bf16) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-                o.x = *reinterpret_cast<uint32_t*>(&lo);
-                o.y = *reinterpret_cast<uint32_t*>(&hi);
-              } else {
-                __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-                o.x = *reinterpret_cast<uint32_t*>(&lo);
-                o.y = *reinterpret_cast<uint32_t*>(&hi);
-              }
-              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)tok * p.ldo + n) = o;
-            }
-          }
-        }
+        epilogue_phase_b(p, stg, lane, token_own, valid_own, n_out_base + c0, n_out_total);
         __syncwarp();
       }
       tc_fence_before();
@@ -330,7 +334,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -412,7 +416,7 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   p.n_tiles = (d->N + d->tile_n - 1) / d->tile_n;
   p.bf16 = d->bf16;
   p.stage_bytes = kABytes + ((d->tile_n * 128 + 1023) / 1024) * 1024;
-  constexpr int kStagingBytes = 4 * 32 * 256;  // epilogue transpose buffers (4 warps x 32 rows x 64 fp32)
+  constexpr int kStagingBytes = 8 * 32 * 128;  // epilogue transpose buffers (8 warps x 32 rows x 32 fp32)
   p.nstages = (227 * 1024 - 2048 - kStagingBytes) / p.stage_bytes;
   if (p.nstages > kMaxStages) p.nstages = kMaxStages;
   p.out = d->out; p.ldo = d->ldo; p.out_f32 = d->out_f32; p.act = d->act;
@@ -432,7 +436,7 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   const long long total = (long long)p.m_tiles * p.n_tiles;
   int grid = device_sm_count();
   if (total < grid) grid = (int)total;
-  tapgemm_kernel<<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
+  tapgemm_kernel<<<grid, 320, smem_bytes, stream>>>(tmA, tmB, p);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -60,17 +60,27 @@ gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_fram
     for (int i = 0; i < 8; ++i) s[j][i] = q[j][i] = 0.f;
   if (row < rows) {
     const __half* base = x + ((long long)frame * tokens_per_frame) * ldx;
-    for (int t = t0 + row; t < t1; t += rows) {
+    // 4 tokens per iteration: 4 independent 16-byte loads in flight per thread and vector
+    for (int t = t0 + row; t < t1; t += 4 * rows) {
 #pragma unroll
       for (int j = 0; j < kGnMaxJ; ++j) {
         const int v = lane + j * L;
         if (j < J && v < nvec) {
-          float f[8];
-          h8_to_f(__ldg(reinterpret_cast<const uint4*>(base + (long long)t * ldx + v * 8)), f);
+          uint4 u[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            s[j][i] += f[i];
-            q[j][i] += f[i] * f[i];
+          for (int k = 0; k < 4; ++k) {
+            const int tt = t + k * rows;
+            u[k] = tt < t1 ? __ldg(reinterpret_cast<const uint4*>(base + (long long)tt * ldx + v * 8)) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float f[8];
+            h8_to_f(u[k], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              s[j][i] += f[i];
+              q[j][i] += f[i] * f[i];
+            }
           }
         }
       }
@@ -152,16 +162,30 @@ gn_apply_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict_
   const int t0 = blockIdx.x * chunk;
   const int n = min(chunk, tokens_per_frame - t0);
   const long long tok0 = (long long)frame * tokens_per_frame + t0;
-  for (int idx = threadIdx.x; idx < n * nvec; idx += blockDim.x) {
-    const int t = idx / nvec, v = idx - t * nvec;
-    float f[8];
-    h8_to_f(__ldg(reinterpret_cast<const uint4*>(x + (tok0 + t) * ldx + v * 8)), f);
+  const int total = n * nvec;
+  for (int idx0 = threadIdx.x; idx0 < total; idx0 += 4 * blockDim.x) {
+    uint4 u[4];
+    int tt[4], vv[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float r = f[i] * sh[v * 8 + i] + sh[C + v * 8 + i];
-      f[i] = silu ? silu_f(r) : r;
+    for (int k = 0; k < 4; ++k) {
+      const int idx = idx0 + k * blockDim.x;
+      tt[k] = idx / nvec;
+      vv[k] = idx - tt[k] * nvec;
+      if (idx < total) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (tok0 + tt[k]) * ldx + vv[k] * 8));
     }
-    *reinterpret_cast<uint4*>(y + (tok0 + t) * ldy + v * 8) = f_to_h8(f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (idx0 + k * blockDim.x < total) {
+        float f[8];
+        h8_to_f(u[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float r = f[i] * sh[vv[k] * 8 + i] + sh[C + vv[k] * 8 + i];
+          f[i] = silu ? silu_f(r) : r;
+        }
+        *reinterpret_cast<uint4*>(y + (tok0 + tt[k]) * ldy + vv[k] * 8) = f_to_h8(f);
+      }
+    }
   }
 }
 

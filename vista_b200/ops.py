@@ -7,6 +7,7 @@ Activations are token-major fp16 ``[tokens, C]`` views (row stride = ``tensor.st
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -169,13 +170,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
     return out
 
 
-def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int):
+ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "2"))   # 2: ping-pong kernel (default), 1: first-generation kernel
+
+
+def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
+    fn = _lib.load().b200v_attention_spatial_v2 if (impl or ATTN_IMPL) == 2 else _lib.load().b200v_attention_spatial
     _count(1)
     _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
                 2.0 * 4 * frames * seq * heads * 64)
-    _lib.check(_lib.load().b200v_attention_spatial(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
-                                                   v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
-                                                   frames, seq, heads, _stream()), "b200v_attention_spatial")
+    _lib.check(fn(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
+                  out.stride(0), frames, seq, heads, _stream()), "b200v_attention_spatial")
     _prof_end()
     _trace("attn_spatial", out)
     return out
