@@ -260,88 +260,163 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// Temporal attention: one block per (clip, pixel, group of 4 heads), one warp per head.  K and V of the T frames
-// (T <= 32, d = 64) sit in shared memory; lane t owns query frame t.  Bandwidth bound.
+// Temporal attention: sequence = the T <= 32 frames of one pixel, head dim 64.  One warp per
+// (clip, pixel, head): q/k/v rows (128 B each, strided over frames) are brought to shared memory with
+// cp.async (all ~20 loads of a lane in flight), S = Q K^T and O = P V run on mma.sync m16n8k16
+// (32 x 32 x 64 and 32 x 64 x 32 with zero padding), softmax in the accumulator fragments.  The kernel is
+// a pure HBM stream: it reads q, k, v and writes o exactly once.
 // ------------------------------------------------------------------------------------------
-__global__ void attn_temporal_kernel(const __half* __restrict__ q, long long ld_q, const __half* __restrict__ k,
-                                     long long ld_k, const __half* __restrict__ v, long long ld_v,
-                                     __half* __restrict__ out, long long ld_o, int T, int S, int heads) {
-  extern __shared__ __half shkv[];  // per warp: K[T][64], V[T][64]
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t h2_bits(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kTaWarps = 4;
+
+__global__ void __launch_bounds__(kTaWarps * 32)
+attn_temporal_kernel(const __half* __restrict__ q, long long ld_q, const __half* __restrict__ k, long long ld_k,
+                     const __half* __restrict__ v, long long ld_v, __half* __restrict__ out, long long ld_o, int nb,
+                     int T, int S, int heads) {
+  __shared__ __align__(128) uint8_t tiles[kTaWarps][3][32 * 128];   // per warp: Q, K, V tiles of 32 rows x 128 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x, b = blockIdx.y;
-  const int head = blockIdx.z * 4 + warp;
-  if (head >= heads) return;
-  __half* sK = shkv + (size_t)warp * 2 * T * 64;
-  __half* sV = sK + T * 64;
-  const long long tok0 = (long long)b * T * S + s;  // token of frame 0; frame t adds t*S
-  // cooperative load: T rows x 8 vectors (16 B) for K and V
-  for (int i = lane; i < T * 8; i += 32) {
-    const int t = i >> 3, c = i & 7;
-    const long long tok = tok0 + (long long)t * S;
-    reinterpret_cast<uint4*>(sK)[i] = __ldg(reinterpret_cast<const uint4*>(k + tok * ld_k + head * 64 + c * 8));
-    reinterpret_cast<uint4*>(sV)[i] = __ldg(reinterpret_cast<const uint4*>(v + tok * ld_v + head * 64 + c * 8));
-  }
+  const uint32_t sQ = smem_u32(tiles[warp][0]), sK = smem_u32(tiles[warp][1]), sV = smem_u32(tiles[warp][2]);
+  // zero the padding rows once (rows >= T are never written afterwards)
+  for (int i = lane; i < 3 * 32 * 8; i += 32) reinterpret_cast<uint4*>(tiles[warp][0])[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
-  if (lane < T) {
-    const long long tok = tok0 + (long long)lane * S;
-    float qf[64];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float f[8];
-      h8_to_f(__ldg(reinterpret_cast<const uint4*>(q + tok * ld_q + head * 64 + c * 8)), f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) qf[c * 8 + i] = f[i] * 0.125f;  // 64^-0.5
+  const long long items = (long long)nb * S * heads;
+  const int quad = lane >> 2, tq = lane & 3;
+  for (long long item = (long long)blockIdx.x * kTaWarps + warp; item < items; item += (long long)gridDim.x * kTaWarps) {
+    const int head = (int)(item % heads);
+    const long long ps = item / heads;
+    const int s = (int)(ps % S);
+    const int b = (int)(ps / S);
+    const long long tok0 = (long long)b * T * S + s;
+    // ---- stage q, k, v rows: chunk c (16 B) of row t goes to slot c ^ (t & 7)
+    for (int i = lane; i < T * 8; i += 32) {
+      const int t = i >> 3, c = i & 7;
+      const long long tok = tok0 + (long long)t * S;
+      const uint32_t off = t * 128 + ((c ^ (t & 7)) << 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sQ + off), "l"(q + tok * ld_q + head * 64 + c * 8) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sK + off), "l"(k + tok * ld_k + head * 64 + c * 8) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sV + off), "l"(v + tok * ld_v + head * 64 + c * 8) : "memory");
     }
-    float sc[32];
-    float mx = -INFINITY;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- S = Q K^T  (rows: 2 m16 tiles, keys: 4 n8 tiles, dims: 4 k16 steps)
+    float sc[2][4][4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      sc[j] = -INFINITY;
-      if (j < T) {
-        float a = 0.f;
-        const __half2* kr = reinterpret_cast<const __half2*>(sK + j * 64);
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int d = 0; d < 32; ++d) {
-          const float2 kk = __half22float2(kr[d]);
-          a = fmaf(qf[2 * d], kk.x, a);
-          a = fmaf(qf[2 * d + 1], kk.y, a);
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[mt][nt][i] = 0.f;
+    {
+      const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8;   // ldmatrix row supplied by this lane (A operand)
+      const int mchk = lane >> 4;                            // 0: k-chunk 2kk, 1: k-chunk 2kk+1
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int row = mt * 16 + mrow, chk = 2 * kk + mchk;
+          ldsm_x4(sQ + row * 128 + ((chk ^ (row & 7)) << 4), a[mt]);
         }
-        sc[j] = a;
-        mx = fmaxf(mx, a);
-      }
-    }
-    float l = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < T) {
-        sc[j] = __expf(sc[j] - mx);
-        l += sc[j];
-      }
-    }
-    const float inv = 1.0f / l;
-    float o[64];
+        for (int nt = 0; nt < 4; nt += 2) {
+          // B fragments of two key tiles: matrices (keys 8nt.., chunk 2kk), (8nt.., 2kk+1), (8(nt+1).., 2kk), (.., 2kk+1)
+          uint32_t bfr[4];
+          const int row = nt * 8 + (lane & 7) + (lane >> 4) * 8, chk = 2 * kk + ((lane >> 3) & 1);
+          ldsm_x4(sK + row * 128 + ((chk ^ (row & 7)) << 4), bfr);
 #pragma unroll
-    for (int d = 0; d < 64; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < T) {
-        const float pj = sc[j] * inv;
-        const __half2* vr = reinterpret_cast<const __half2*>(sV + j * 64);
-#pragma unroll
-        for (int d = 0; d < 32; ++d) {
-          const float2 vv = __half22float2(vr[d]);
-          o[2 * d] = fmaf(pj, vv.x, o[2 * d]);
-          o[2 * d + 1] = fmaf(pj, vv.y, o[2 * d + 1]);
+          for (int mt = 0; mt < 2; ++mt) {
+            mma_16816(sc[mt][nt], a[mt], bfr[0], bfr[1]);
+            mma_16816(sc[mt][nt + 1], a[mt], bfr[2], bfr[3]);
+          }
         }
       }
     }
+    // ---- softmax over keys (< T), rows live in quads: cols 8nt + 2tq + {0,1}; regs {0,1}: row quad, {2,3}: row quad+8
+    uint32_t pa[2][2][4];   // P as A fragments: [mt][k16 step][4]
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float f[8];
+    for (int mt = 0; mt < 2; ++mt) {
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = o[c * 8 + i];
-      *reinterpret_cast<uint4*>(out + tok * ld_o + head * 64 + c * 8) = f_to_h8(f);
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int key = nt * 8 + 2 * tq + (i & 1);
+          float x = key < T ? sc[mt][nt][i] * 0.125f : -INFINITY;
+          sc[mt][nt][i] = x;
+          if (i < 2) mx0 = fmaxf(mx0, x); else mx1 = fmaxf(mx1, x);
+        }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float e = __expf(sc[mt][nt][i] - (i < 2 ? mx0 : mx1));
+          sc[mt][nt][i] = e;
+          if (i < 2) l0 += e; else l1 += e;
+        }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        pa[mt][k2][0] = h2_bits(sc[mt][2 * k2][0] * i0, sc[mt][2 * k2][1] * i0);
+        pa[mt][k2][1] = h2_bits(sc[mt][2 * k2][2] * i1, sc[mt][2 * k2][3] * i1);
+        pa[mt][k2][2] = h2_bits(sc[mt][2 * k2 + 1][0] * i0, sc[mt][2 * k2 + 1][1] * i0);
+        pa[mt][k2][3] = h2_bits(sc[mt][2 * k2 + 1][2] * i1, sc[mt][2 * k2 + 1][3] * i1);
+      }
     }
+    // ---- O = P V  (dims: 8 n8 tiles, keys: 2 k16 steps); V^T fragments via ldmatrix.trans
+    __syncwarp();   // every lane is done reading Q: its tile is reused to stage O
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      uint32_t bfr[4];
+      const int row = lane;   // matrices 0..3 = keys 0-7, 8-15, 16-23, 24-31; all take 16-byte chunk dt
+      ldsm_x4_trans(sV + row * 128 + ((dt ^ (row & 7)) << 4), bfr);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_16816(o, pa[mt][0], bfr[0], bfr[1]);
+        mma_16816(o, pa[mt][1], bfr[2], bfr[3]);
+        // stage: rows mt*16 + quad (+8), dims 8dt + 2tq + {0,1}  -> 4-byte pieces of chunk dt
+        const int r0 = mt * 16 + quad, r1 = r0 + 8;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + r0 * 128 + ((dt ^ (r0 & 7)) << 4) + tq * 4), "r"(h2_bits(o[0], o[1])) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + r1 * 128 + ((dt ^ (r1 & 7)) << 4) + tq * 4), "r"(h2_bits(o[2], o[3])) : "memory");
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < T * 8; i += 32) {
+      const int t = i >> 3, c = i & 7;
+      const long long tok = tok0 + (long long)t * S;
+      uint4 val;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                   : "r"(sQ + t * 128 + ((c ^ (t & 7)) << 4)));
+      *reinterpret_cast<uint4*>(out + tok * ld_o + head * 64 + c * 8) = val;
+    }
+    __syncwarp();   // O staging fully read before the next item's cp.async overwrite the Q tile
   }
 }
 
@@ -693,11 +768,12 @@ extern "C" int b200v_attention_temporal(const void* q, int64_t ld_q, const void*
   VB_REQUIRE(q && k && v && out, "attention_temporal: null pointer");
   VB_REQUIRE(T >= 1 && T <= 32 && heads >= 1, "attention_temporal: T=%d heads=%d unsupported", T, heads);
   VB_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 8 == 0, "attention_temporal: bad ld");
-  const size_t smem = (size_t)4 * 2 * T * 64 * sizeof(__half);
-  dim3 grid(S, nb, (heads + 3) / 4);
-  attn_temporal_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const __half*)q, ld_q, (const __half*)k, ld_k,
-                                                                         (const __half*)v, ld_v, (__half*)out, ld_o, T,
-                                                                         S, heads);
+  const long long items = (long long)nb * S * heads;
+  long long blocks = (items + kTaWarps - 1) / kTaWarps;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  attn_temporal_kernel<<<(unsigned)blocks, kTaWarps * 32, 0, (cudaStream_t)stream>>>(
+      (const __half*)q, ld_q, (const __half*)k, ld_k, (const __half*)v, ld_v, (__half*)out, ld_o, nb, T, S, heads);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
