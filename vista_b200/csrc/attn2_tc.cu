@@ -62,13 +62,28 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
   return m;
 }
+// exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.7e-5, below the fp16 rounding of P), exponent patched in with one
+// shift-add.  Used for a fraction of the elements so that the MUFU (16 ex2/clk/SM) stops being the bound.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.05508868396282196f, f, 0.24260404706001282f);
+  p = fmaf(p, f, 0.6932762265205383f);
+  p = fmaf(p, f, 0.9999289512634277f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef VB_ATTN_POLY_OF_4
+#define VB_ATTN_POLY_OF_4 2   // how many of every 4 exponentials go to the polynomial path
+#endif
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t p;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
   return p;
 }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __maxnreg__(200)
 attn2_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -210,9 +225,14 @@ attn2_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int i = 0; i < 128; ++i)
           if (i >= kv_left) s[i] = 0xFF800000u;  // -inf
       }
-      float mx = -INFINITY;
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent chains
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) mx = max3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+      for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          mxa[u] = max3(mxa[u], __uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1]));
+      }
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       const float m_blk = mx * p.scale_log2;
       // lazy rescale: only when the block maximum exceeds the maximum in use by more than 8 (factor 256)
       const bool need = m_blk > m_used + 8.0f;
@@ -239,8 +259,10 @@ attn2_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float p0 = ex2_f(fmaf(__uint_as_float(s[c * 8 + 2 * i]), p.scale_log2, -m_used));
-          const float p1 = ex2_f(fmaf(__uint_as_float(s[c * 8 + 2 * i + 1]), p.scale_log2, -m_used));
+          const float x0 = fmaf(__uint_as_float(s[c * 8 + 2 * i]), p.scale_log2, -m_used);
+          const float x1 = fmaf(__uint_as_float(s[c * 8 + 2 * i + 1]), p.scale_log2, -m_used);
+          const float p0 = (i < VB_ATTN_POLY_OF_4) ? exp2_poly(x0) : ex2_f(x0);
+          const float p1 = (i < VB_ATTN_POLY_OF_4) ? exp2_poly(x1) : ex2_f(x1);
           w[i] = pack_h2(p0, p1);
         }
         const uint32_t addr = p_row + (c >> 3) * kT2Bytes + (((c & 7) ^ sw) << 4);

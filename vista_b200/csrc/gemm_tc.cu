@@ -88,19 +88,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
 
 // Phase B of the epilogue: the warp walks its 32 staged rows (32 fp32 columns = 8 chunks of 16 bytes per row,
 // 4 rows per instruction) so that every residual load / output store covers a contiguous 64-byte (fp16) or
-// 128-byte (fp32) row segment.  All 8 iterations are batched: loads are issued before the first use.
-__device__ __forceinline__ void epilogue_phase_b(const TGParams& p, uint32_t stg, int lane, int token_own, int valid_own,
-                                                 int n_base, int n_out_total) {
+// 128-byte (fp32) row segment.  The first residual was prefetched into registers before the accumulator was
+// ready (u1); a second residual (AlphaBlender GEMMs only) is loaded here, batched ahead of its use.
+__device__ __forceinline__ void epilogue_phase_b(const TGParams& p, uint32_t stg, int lane, const int (&tok)[8],
+                                                 const bool (&okr)[8], const uint2 (&u1)[8], int n, bool n_ok) {
   const int ch = lane & 7;
   const int rsub = lane >> 3;
-  const int n = n_base + ch * 4;
-  const bool n_ok = n + 4 <= n_out_total;
-  const uint16_t* r1p = reinterpret_cast<const uint16_t*>(p.res1);
   const uint16_t* r2p = reinterpret_cast<const uint16_t*>(p.res2);
   float4 v[8];
-  uint2 u1[8], u2[8];
-  int tok[8];
-  bool ok[8];
+  uint2 u2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = i * 4 + rsub;
@@ -108,18 +104,14 @@ __device__ __forceinline__ void epilogue_phase_b(const TGParams& p, uint32_t stg
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
                  : "r"(stg + row * 128 + slot * 16));
-    tok[i] = __shfl_sync(0xffffffffu, token_own, row);
-    ok[i] = (__shfl_sync(0xffffffffu, valid_own, row) != 0) && n_ok;
-    u1[i] = make_uint2(0, 0);
     u2[i] = make_uint2(0, 0);
-    if (r1p && ok[i]) u1[i] = __ldg(reinterpret_cast<const uint2*>(r1p + (long long)tok[i] * p.ld_res1 + n));
-    if (r2p && ok[i]) u2[i] = __ldg(reinterpret_cast<const uint2*>(r2p + (long long)tok[i] * p.ld_res2 + n));
+    if (r2p && okr[i] && n_ok) u2[i] = __ldg(reinterpret_cast<const uint2*>(r2p + (long long)tok[i] * p.ld_res2 + n));
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (!ok[i]) continue;
+    if (!(okr[i] && n_ok)) continue;
     float4 o = v[i];
-    if (r1p) {
+    if (p.res1) {
       const float2 a = unpack2(u1[i].x, p.bf16), b = unpack2(u1[i].y, p.bf16);
       o.x += p.s_res1 * a.x; o.y += p.s_res1 * a.y; o.z += p.s_res1 * b.x; o.w += p.s_res1 * b.y;
     }
@@ -136,7 +128,7 @@ __device__ __forceinline__ void epilogue_phase_b(const TGParams& p, uint32_t stg
   }
 }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __maxnreg__(200)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -269,10 +261,40 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const float* rv_ptr = p.rowvec ? p.rowvec + (long long)((token_own / p.rv_div) % p.rv_mod) * p.ld_rowvec : nullptr;
       const int n_out_base = n_blk * tile_out_cols;
+      // rows this lane serves in phase B (4 rows per instruction, 8 instructions) and their tokens
+      int tok[8];
+      bool okr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3);
+        tok[i] = __shfl_sync(0xffffffffu, token_own, row);
+        okr[i] = __shfl_sync(0xffffffffu, valid_own, row) != 0;
+      }
+      // prefetch the first residual of all column groups of this warp while the MMAs of the tile still run.
+      // Group order per warpgroup: {2wg, 2wg+1, 4+2wg, 4+2wg+1}: both 64-byte halves of an output line are
+      // written back to back by the same warp.
+      uint2 rpre[4][8];
+      if (p.res1) {
+        const uint16_t* r1p = reinterpret_cast<const uint16_t*>(p.res1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c0 = ((k >> 1) * 4 + wg * 2 + (k & 1)) * 32;
+          const int n = n_out_base + c0 + (lane & 7) * 4;
+          const bool n_ok = (c0 < tile_out_cols) && (n + 4 <= n_out_total);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rpre[k][i] = make_uint2(0, 0);
+            if (n_ok && okr[i]) rpre[k][i] = __ldg(reinterpret_cast<const uint2*>(r1p + (long long)tok[i] * p.ld_res1 + n));
+          }
+        }
+      }
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
-      for (int c0 = wg * 32; c0 < tile_out_cols; c0 += 64) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c0 = ((k >> 1) * 4 + wg * 2 + (k & 1)) * 32;
+        if (c0 >= tile_out_cols) break;
         // ---------------- phase A
         float f[32];
         if (p.act != 2) {
@@ -323,7 +345,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         // ---------------- phase B
-        epilogue_phase_b(p, stg, lane, token_own, valid_own, n_out_base + c0, n_out_total);
+        {
+          const int n = n_out_base + c0 + (lane & 7) * 4;
+          epilogue_phase_b(p, stg, lane, tok, okr, rpre[k], n, n + 4 <= n_out_total);
+        }
         __syncwarp();
       }
       tc_fence_before();

@@ -30,27 +30,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires, so the
+  // waiting producer / MMA lanes do not steal issue slots from the epilogue / softmax warps of their SM sub-partition
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must end in a trap (test failure), never in a hung GPU box.
+// Bounded wait: a pipeline bug must end in a trap (test failure), never in a hung GPU box.  The clock is
+// consulted only every 4096 failed probes.
 #ifndef VB_WAIT_TIMEOUT_CYCLES
 #define VB_WAIT_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > VB_WAIT_TIMEOUT_CYCLES) {
-      printf("vista_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, parity);
-      __trap();
+  long long t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 4095u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > VB_WAIT_TIMEOUT_CYCLES) {
+        printf("vista_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
+               blockIdx.y, blockIdx.z, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -163,20 +171,20 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int bf
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // erf-GELU via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7; measured |gelu error| <= 4.3e-7, below the
-// fp16 rounding of the output): erfc(a) = poly(t) * exp(-a^2), t = 1/(1 + p a).  2 MUFU + ~12 FMA.
+// fp16 rounding of the output): erfc(a) = poly(t) * exp(-a^2), t = 1/(1 + p a), a = |x|/sqrt(2).
+// gelu(x) = x<0 ? h*erfc : x - h*erfc with h = x/2.  2 MUFU + ~13 FMA-pipe operations.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);
   poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-(ax * ax) * 1.4426950408889634f));
-  const float pe = poly * e;                       // erfc(|x|/sqrt2)
-  const float one_plus_erf = x < 0.0f ? pe : 2.0f - pe;
-  return 0.5f * x * one_plus_erf;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * (ax * -1.4426950408889634f)));
+  const float r = (0.5f * x) * ((poly * t) * e);   // h * erfc(|x|/sqrt2)
+  return x < 0.0f ? r : x - r;
 }
 __device__ __forceinline__ float ex2_f(float x) {
   float y;
