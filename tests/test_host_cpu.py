@@ -165,3 +165,26 @@ def test_synth_is_platform_stable():
     assert synth.checksum([a]) == synth.checksum([synth.normal(1, "x", (4,))])
     sd = synth.synth_state_dict(spec.unet_param_specs(spec.unet_preset("tiny")), seed=1)
     assert synth.state_dict_checksum(sd) == str(np.load(os.path.join(ROOT, "tests", "golden", "unet_tiny.npz"))["weight_checksum"])
+
+
+def test_kernel_register_budgets_fit_their_launch_shape():
+    """A kernel whose registers x threads (at the 512-register-per-warp allocation granularity) exceed the
+    64 K register file fails at launch with 'too many resources' — check it at build time, without a GPU."""
+    import subprocess
+    from vista_b200 import lib
+    lib.build()
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", lib.LIB_PATH], capture_output=True, text=True).stdout
+    blocks = {"tapgemm_kernel": 320, "attn2_spatial_kernel": 320, "attn_spatial_kernel": 192, "attn_temporal_kernel": 128,
+              "gn_stats_kernel": 256, "gn_apply_kernel": 256, "layernorm_kernel": 256}
+    found = 0
+    lines = out.splitlines()
+    for i, line in enumerate(lines):
+        for name, threads in blocks.items():
+            if "Function" in line and name in line:
+                m = re.search(r"REG:(\d+)", lines[i + 1])
+                assert m, lines[i + 1]
+                regs = int(m.group(1))
+                per_warp = -(-regs * 32 // 512) * 512
+                assert per_warp * (threads // 32) <= 65536, (name, regs, threads)
+                found += 1
+    assert found >= 7

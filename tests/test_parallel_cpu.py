@@ -1,0 +1,52 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank host logic."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vista_b200 import parallel as par
+
+
+def test_shard_arithmetic():
+    assert [len(par.shard_units(25, 8, r)) for r in range(8)] == [4, 3, 3, 3, 3, 3, 3, 3]
+    assert par.frame_shards(25, 2) == [(0, 13), (13, 25)]
+    cover = [t for a, b in par.frame_shards(25, 8) for t in range(a, b)]
+    assert cover == list(range(25))
+    assert par.halo_neighbours(0, 4) == (None, 1) and par.halo_neighbours(3, 4) == (2, None)
+    assert [list(par.shard_units(5, 2, r)) for r in range(2)] == [[0, 1, 2], [3, 4]]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T = 25
+        full = torch.arange(T * 6, dtype=torch.float32).reshape(T, 2, 3)
+        a, b = par.frame_shards(T, world)[rank]
+        got = par.gather_frames(full[a:b].clone(), T)
+        ok_gather = torch.equal(got, full)
+        t = par.max_over_ranks(1.0 + rank)
+        stats = torch.tensor([[1.0 + rank, 2.0 * (rank + 1)]], dtype=torch.float64)
+        tot = par.reduce_group_stats(stats)
+        q.put((rank, ok_gather, t, tot.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_collectives():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_gather, t, tot in res:
+        assert ok_gather
+        assert t == 2.0                      # max over ranks
+        assert tot == [[3.0, 6.0]]           # 1+2, 2+4: identical on both ranks

@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return p;
 }
 
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 attn2_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
   extern __shared__ uint8_t smem_raw[];

@@ -128,7 +128,7 @@ __device__ __forceinline__ void epilogue_phase_b(const TGParams& p, uint32_t stg
   }
 }
 
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
