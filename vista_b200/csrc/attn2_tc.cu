@@ -83,7 +83,8 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return p;
 }
 
-__global__ void __maxnreg__(192)
+// 10 warps are allocated as 12 (granularity 4): at most 168 registers per thread
+__global__ void __launch_bounds__(320, 1)
 attn2_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
   extern __shared__ uint8_t smem_raw[];

@@ -128,7 +128,8 @@ __device__ __forceinline__ void epilogue_phase_b(const TGParams& p, uint32_t stg
   }
 }
 
-__global__ void __maxnreg__(192)
+// 10 warps are allocated as 12 (granularity 4): 65536 / 384 -> at most 168 registers per thread
+__global__ void __launch_bounds__(320, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -270,24 +271,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tok[i] = __shfl_sync(0xffffffffu, token_own, row);
         okr[i] = __shfl_sync(0xffffffffu, valid_own, row) != 0;
       }
-      // prefetch the first residual of all column groups of this warp while the MMAs of the tile still run.
-      // Group order per warpgroup: {2wg, 2wg+1, 4+2wg, 4+2wg+1}: both 64-byte halves of an output line are
-      // written back to back by the same warp.
-      uint2 rpre[4][8];
-      if (p.res1) {
-        const uint16_t* r1p = reinterpret_cast<const uint16_t*>(p.res1);
+      // The first residual is prefetched into registers one column group ahead (group 0 while the MMAs of the
+      // tile still run).  Group order per warpgroup: {2wg, 2wg+1, 4+2wg, 4+2wg+1}: both 64-byte halves of an
+      // output line are written back to back by the same warp.
+      uint2 rpre[2][8];
+      const uint16_t* r1p = reinterpret_cast<const uint16_t*>(p.res1);
+      auto prefetch_res = [&](int k, uint2 (&dst)[8]) {
+        const int c0 = ((k >> 1) * 4 + wg * 2 + (k & 1)) * 32;
+        const int n = n_out_base + c0 + (lane & 7) * 4;
+        const bool n_ok = (c0 < tile_out_cols) && (n + 4 <= n_out_total);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c0 = ((k >> 1) * 4 + wg * 2 + (k & 1)) * 32;
-          const int n = n_out_base + c0 + (lane & 7) * 4;
-          const bool n_ok = (c0 < tile_out_cols) && (n + 4 <= n_out_total);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            rpre[k][i] = make_uint2(0, 0);
-            if (n_ok && okr[i]) rpre[k][i] = __ldg(reinterpret_cast<const uint2*>(r1p + (long long)tok[i] * p.ld_res1 + n));
-          }
+        for (int i = 0; i < 8; ++i) {
+          dst[i] = make_uint2(0, 0);
+          if (r1p && n_ok && okr[i]) dst[i] = __ldg(reinterpret_cast<const uint2*>(r1p + (long long)tok[i] * p.ld_res1 + n));
         }
-      }
+      };
+      prefetch_res(0, rpre[0]);
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
@@ -295,6 +294,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int k = 0; k < 4; ++k) {
         const int c0 = ((k >> 1) * 4 + wg * 2 + (k & 1)) * 32;
         if (c0 >= tile_out_cols) break;
+        if (k + 1 < 4) prefetch_res(k + 1, rpre[(k + 1) & 1]);
         // ---------------- phase A
         float f[32];
         if (p.act != 2) {
@@ -347,7 +347,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---------------- phase B
         {
           const int n = n_out_base + c0 + (lane & 7) * 4;
-          epilogue_phase_b(p, stg, lane, tok, okr, rpre[k], n, n + 4 <= n_out_total);
+          epilogue_phase_b(p, stg, lane, tok, okr, rpre[k & 1], n, n + 4 <= n_out_total);
         }
         __syncwarp();
       }

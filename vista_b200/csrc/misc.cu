@@ -39,8 +39,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // floating-point atomics, no memset (the counter resets itself).
 // ------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
-constexpr int kGnMaxJ = 4;  // vectors per thread (C <= 8 * L * kGnMaxJ)
+constexpr int kGnMaxJ = 4;  // max vectors per thread (C <= 8 * 256 * kGnMaxJ); kernels are templated on 1 / 2 / 4
 
+template <int JT>
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_frame, int C, int groups,
                 int frames_per_stat, int chunk, int L, int J, float eps, double* __restrict__ partials,
@@ -53,9 +54,9 @@ gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_fram
   const int nvec = C >> 3;
   const int rows = kGnThreads / L;
   const int lane = threadIdx.x % L, row = threadIdx.x / L;
-  float s[kGnMaxJ][8], q[kGnMaxJ][8];
+  float s[JT][8], q[JT][8];
 #pragma unroll
-  for (int j = 0; j < kGnMaxJ; ++j)
+  for (int j = 0; j < JT; ++j)
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[j][i] = q[j][i] = 0.f;
   if (row < rows) {
@@ -63,7 +64,7 @@ gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_fram
     // 4 tokens per iteration: 4 independent 16-byte loads in flight per thread and vector
     for (int t = t0 + row; t < t1; t += 4 * rows) {
 #pragma unroll
-      for (int j = 0; j < kGnMaxJ; ++j) {
+      for (int j = 0; j < JT; ++j) {
         const int v = lane + j * L;
         if (j < J && v < nvec) {
           uint4 u[4];
@@ -87,7 +88,7 @@ gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_fram
     }
     float* mine = sh + (size_t)row * 2 * C;
 #pragma unroll
-    for (int j = 0; j < kGnMaxJ; ++j) {
+    for (int j = 0; j < JT; ++j) {
       const int v = lane + j * L;
       if (j < J && v < nvec) {
 #pragma unroll
@@ -141,49 +142,66 @@ gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_fram
   if (threadIdx.x == 0) counters[stat] = 0;  // ready for the next launch
 }
 
-// apply: grid = (chunks, frames); y = (x-mean)*rstd*gamma + beta, optional SiLU
-__global__ void __launch_bounds__(256)
+// apply: grid = (chunks, frames); y = (x-mean)*rstd*gamma + beta, optional SiLU.  Same thread layout as the
+// statistics kernel: thread (row, lane) owns channel vectors lane, lane+L, ... so the per-channel scale / shift
+// live in registers; 4 tokens per iteration keep 4 loads in flight per vector.
+template <int JT>
+__global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
-                int tokens_per_frame, int C, int groups, int frames_per_stat, int chunk,
+                int tokens_per_frame, int C, int groups, int frames_per_stat, int chunk, int L, int J,
                 const float* __restrict__ mean_rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                 int silu) {
-  extern __shared__ float sh[];  // scale[C], shift[C]
   const int frame = blockIdx.y;
   const int cpg = C / groups;
-  const float* st = mean_rstd + (long long)(frame / frames_per_stat) * groups * 2;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float sc = st[2 * g + 1] * gamma[c];
-    sh[c] = sc;
-    sh[C + c] = beta[c] - st[2 * g] * sc;
-  }
-  __syncthreads();
   const int nvec = C >> 3;
-  const int t0 = blockIdx.x * chunk;
-  const int n = min(chunk, tokens_per_frame - t0);
-  const long long tok0 = (long long)frame * tokens_per_frame + t0;
-  const int total = n * nvec;
-  for (int idx0 = threadIdx.x; idx0 < total; idx0 += 4 * blockDim.x) {
-    uint4 u[4];
-    int tt[4], vv[4];
+  const int rows = kGnThreads / L;
+  const int lane = threadIdx.x % L, row = threadIdx.x / L;
+  if (row >= rows) return;
+  const float* st = mean_rstd + (long long)(frame / frames_per_stat) * groups * 2;
+  float sc[JT][8], sf[JT][8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int idx = idx0 + k * blockDim.x;
-      tt[k] = idx / nvec;
-      vv[k] = idx - tt[k] * nvec;
-      if (idx < total) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (tok0 + tt[k]) * ldx + vv[k] * 8));
+  for (int j = 0; j < JT; ++j) {
+    const int v = lane + j * L;
+    if (j < J && v < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = v * 8 + i;
+        const int g = c / cpg;
+        const float s_ = __ldg(st + 2 * g + 1) * __ldg(gamma + c);
+        sc[j][i] = s_;
+        sf[j][i] = __ldg(beta + c) - __ldg(st + 2 * g) * s_;
+      }
     }
+  }
+  const int t0 = blockIdx.x * chunk;
+  const int t1 = min(t0 + chunk, tokens_per_frame);
+  const __half* xb = x + ((long long)frame * tokens_per_frame) * ldx;
+  __half* yb = y + ((long long)frame * tokens_per_frame) * ldy;
+  for (int t = t0 + row; t < t1; t += 4 * rows) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (idx0 + k * blockDim.x < total) {
-        float f[8];
-        h8_to_f(u[k], f);
+    for (int j = 0; j < JT; ++j) {
+      const int v = lane + j * L;
+      if (j < J && v < nvec) {
+        uint4 u[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float r = f[i] * sh[vv[k] * 8 + i] + sh[C + vv[k] * 8 + i];
-          f[i] = silu ? silu_f(r) : r;
+        for (int k = 0; k < 4; ++k) {
+          const int tt = t + k * rows;
+          if (tt < t1) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)tt * ldx + v * 8));
         }
-        *reinterpret_cast<uint4*>(y + (tok0 + tt[k]) * ldy + vv[k] * 8) = f_to_h8(f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int tt = t + k * rows;
+          if (tt < t1) {
+            float f[8];
+            h8_to_f(u[k], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float r = fmaf(f[i], sc[j][i], sf[j][i]);
+              f[i] = silu ? silu_f(r) : r;
+            }
+            *reinterpret_cast<uint4*>(yb + (long long)tt * ldy + v * 8) = f_to_h8(f);
+          }
+        }
       }
     }
   }
@@ -710,13 +728,20 @@ extern "C" int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames,
   const size_t smem = (size_t)rows * 2 * C * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
   VB_REQUIRE(smem <= 160 * 1024, "groupnorm_stats: shared memory %zu too large", smem);
-  gn_stats_kernel<<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, tokens_per_frame, C, groups, frames_per_stat, chunk, L, J, eps, partials, counters,
-      mean_rstd);
+#define VB_GN_STATS(JT)                                                                                              \
+  gn_stats_kernel<JT><<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(                                             \
+      (const __half*)x, ldx, tokens_per_frame, C, groups, frames_per_stat, chunk, L, J, eps, partials, counters,     \
+      mean_rstd)
+  if (J == 1) VB_GN_STATS(1);
+  else if (J == 2) VB_GN_STATS(2);
+  else VB_GN_STATS(4);
+#undef VB_GN_STATS
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -730,11 +755,23 @@ extern "C" int b200v_groupnorm_apply(const void* x, int64_t ldx, void* y, int64_
   VB_REQUIRE(x && y && mean_rstd && gamma && beta, "groupnorm_apply: null pointer");
   VB_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_apply: bad C/ld");
   VB_REQUIRE(frames_per_stat > 0 && frames % frames_per_stat == 0, "groupnorm_apply: frames %% frames_per_stat != 0");
-  const int chunk = 64;
+  const int nvec = C / 8;
+  int L = nvec, J = 1;
+  while (L > kGnThreads) {
+    ++J;
+    L = (nvec + J - 1) / J;
+  }
+  VB_REQUIRE(J <= kGnMaxJ, "groupnorm_apply: C=%d too large", C);
+  const int chunk = 128;
   dim3 grid((tokens_per_frame + chunk - 1) / chunk, frames);
-  gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, (__half*)y, ldy, tokens_per_frame, C, groups, frames_per_stat, chunk, mean_rstd, gamma,
-      beta, silu);
+#define VB_GN_APPLY(JT)                                                                                              \
+  gn_apply_kernel<JT><<<grid, kGnThreads, 0, (cudaStream_t)stream>>>(                                                \
+      (const __half*)x, ldx, (__half*)y, ldy, tokens_per_frame, C, groups, frames_per_stat, chunk, L, J, mean_rstd,  \
+      gamma, beta, silu)
+  if (J == 1) VB_GN_APPLY(1);
+  else if (J == 2) VB_GN_APPLY(2);
+  else VB_GN_APPLY(4);
+#undef VB_GN_APPLY
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
