@@ -92,6 +92,11 @@ int b200v_attention_spatial(const void* q, int64_t ld_q, const void* k, int64_t 
 int b200v_attention_spatial_v2(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                                void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
+/* Third generation: one 128-query tile per CTA, two CTAs per SM, two threads per query row (eight softmax
+ * warps), S consumed in 32-column chunks, part of the exponentials on the FMA pipe. */
+int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                               void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
+
 /* Temporal self-attention over the T frames of each pixel (seq len T <= 32, head dim 64).
  * Replaces the batchified xformers call at vwm/modules/attention.py:384-399 reached from
  * vwm/modules/video_attention.py:127 and both "(b t) s c <-> (b s) t c" rearranges (:116,:140):

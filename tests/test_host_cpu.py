@@ -174,7 +174,7 @@ def test_kernel_register_budgets_fit_their_launch_shape():
     from vista_b200 import lib
     lib.build()
     out = subprocess.run(["cuobjdump", "--dump-resource-usage", lib.LIB_PATH], capture_output=True, text=True).stdout
-    blocks = {"tapgemm_kernel": 320, "attn2_spatial_kernel": 320, "attn_spatial_kernel": 192, "attn_temporal_kernel": 128,
+    blocks = {"tapgemm_kernel": 320, "attn2_spatial_kernel": 320, "attn3_spatial_kernel": 768, "attn_spatial_kernel": 192, "attn_temporal_kernel": 128,
               "gn_stats_kernel": 256, "gn_apply_kernel": 256, "layernorm_kernel": 256}
     found = 0
     lines = out.splitlines()

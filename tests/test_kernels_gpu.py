@@ -141,7 +141,7 @@ def test_gemm_temporal_conv(ops, nb, T, S, Cc):
 
 
 # ------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("frames,seq,heads", [(2, 128, 1), (3, 144, 2), (2, 576, 4), (1, 2304, 2), (2, 200, 1), (1, 256, 1),
                                               (2, 300, 1)])
 def test_attention_spatial(ops, frames, seq, heads, impl):
@@ -155,7 +155,7 @@ def test_attention_spatial(ops, frames, seq, heads, impl):
     check(out, ref, rtol=4e-3, atol=2e-3, name="attn spatial")
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 def test_attention_spatial_peaky(ops, impl):
     """Large logits: the running max / (lazy) rescale path must hold (scores ~ +-40)."""
     frames, seq, heads = 1, 640, 1
@@ -168,7 +168,8 @@ def test_attention_spatial_peaky(ops, impl):
     check(out, ref, rtol=1e-2, atol=1e-2, name="attn peaky")
 
 
-def test_attention_spatial_increasing_max(ops):
+@pytest.mark.parametrize("impl", [2, 3])
+def test_attention_spatial_increasing_max(ops, impl):
     """Keys ordered so that the row maximum keeps growing block after block: exercises every lazy-rescale branch."""
     seq = 1024
     g = torch.Generator().manual_seed(3)
@@ -177,7 +178,7 @@ def test_attention_spatial_increasing_max(ops):
     v = torch.randn(seq, 64, generator=g)
     qkv = torch.cat([q, k, v], 1).half().to(dev())
     out = torch.zeros(seq, 64, dtype=torch.float16, device=dev())
-    ops.attention_spatial(qkv[:, :64], qkv[:, 64:128], qkv[:, 128:], out, 1, seq, 1, impl=2)
+    ops.attention_spatial(qkv[:, :64], qkv[:, 64:128], qkv[:, 128:], out, 1, seq, 1, impl=impl)
     torch.cuda.synchronize()
     qq, kk, vv = (t.float().reshape(1, seq, 1, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
     ref = F.scaled_dot_product_attention(qq, kk, vv).permute(0, 2, 1, 3).reshape(seq, 64)

@@ -95,6 +95,7 @@ SIGNATURES = {
     "b200v_gemm": [C.POINTER(GemmDesc), _P],
     "b200v_attention_spatial": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v2": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
+    "b200v_attention_spatial_v3": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_groupnorm_chunk": [],
     "b200v_groupnorm_stats": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _P],

@@ -174,7 +174,8 @@ ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "2"))   # 2: ping-pong kernel 
 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
-    fn = _lib.load().b200v_attention_spatial_v2 if (impl or ATTN_IMPL) == 2 else _lib.load().b200v_attention_spatial
+    l = _lib.load()
+    fn = {1: l.b200v_attention_spatial, 2: l.b200v_attention_spatial_v2, 3: l.b200v_attention_spatial_v3}[impl or ATTN_IMPL]
     _count(1)
     _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
                 2.0 * 4 * frames * seq * heads * 64)
