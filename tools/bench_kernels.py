@@ -23,6 +23,14 @@ def timeit(name, fn, flops=0.0, nbytes=0.0, reps=5):
     print(f"{name:46s} {ms:8.3f} ms  {flops / ms / 1e9:8.0f} TFLOP/s  {nbytes / ms / 1e6:8.0f} GB/s", flush=True)
 
 
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+_timeit = timeit
+def timeit(name, fn, *a, **k):
+    if only and only not in name:
+        return
+    _timeit(name, fn, *a, **k)
+
+
 for (M, C, geom) in ((460800, 320, (128, 72, 50)), (115200, 640, (64, 36, 50))):
     x = (torch.randn(M, C, device=dev) * 0.5).half()
     w = torch.randn(8 * C, C, device=dev) * C ** -0.5
@@ -46,7 +54,7 @@ for (M, C, geom) in ((460800, 320, (128, 72, 50)), (115200, 640, (64, 36, 50))):
     heads, seq = C // 64, geom[0] * geom[1]
     o = torch.empty(M, C, dtype=torch.float16, device=dev)
     qkv = torch.randn(M, 3 * C, device=dev).half()
-    for impl in (1, 2, 3):
+    for impl in ((3,) if only else (1, 2, 3)):
         timeit(f"attention spatial v{impl} seq={seq} heads={heads}",
                lambda: ops.attention_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, 50, seq, heads, impl=impl),
                4.0 * 64 * heads * 50 * seq * seq, 2.0 * 4 * M * C, reps=3)

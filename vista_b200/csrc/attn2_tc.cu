@@ -359,6 +359,7 @@ namespace vb {
 #define VB_ATTN3_POLY_OF_8 3   // of every 8 exponentials, this many use exp2_poly (FMA pipe) instead of MUFU
 #endif
 
+template <int POLY8>
 __global__ void __launch_bounds__(384, 2)
 attn3_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
@@ -539,8 +540,8 @@ attn3_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int e0 = q4 * 8 + 2 * i, e1 = e0 + 1;
             const float x0 = fmaf(__uint_as_float(s[e0]), p.scale_log2, -m_used);
             const float x1 = fmaf(__uint_as_float(s[e1]), p.scale_log2, -m_used);
-            const float p0 = ((e0 & 7) < VB_ATTN3_POLY_OF_8) ? exp2_poly(x0) : ex2_f(x0);
-            const float p1 = ((e1 & 7) < VB_ATTN3_POLY_OF_8) ? exp2_poly(x1) : ex2_f(x1);
+            const float p0 = ((e0 & 7) < POLY8) ? exp2_poly(x0) : ex2_f(x0);
+            const float p1 = ((e1 & 7) < POLY8) ? exp2_poly(x1) : ex2_f(x1);
             w[i] = pack_h2(p0, p1);
           }
           const int chunk = c * 4 + q4;
@@ -611,13 +612,20 @@ extern "C" int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const voi
   p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   const int smem_bytes = 1024 + 3072 + 6 * kT2Bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
+  static int poly = -1;
+  if (poly < 0) {
+    poly = VB_ATTN3_POLY_OF_8;
+    if (const char* e = getenv("VB_ATTN3_POLY")) poly = atoi(e);   // tuning knob: exponentials (of 8) on the FMA pipe
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
   dim3 grid((seq + kT2 - 1) / kT2, heads, frames);
-  attn3_spatial_kernel<<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  if (poly <= 0) attn3_spatial_kernel<0><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  else if (poly <= 2) attn3_spatial_kernel<2><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  else if (poly == 3) attn3_spatial_kernel<3><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  else attn3_spatial_kernel<4><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -86,6 +86,23 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// Column-group schedule of the two epilogue warpgroups.  G 32-column groups per tile; adjacent groups (2i, 2i+1)
+// form a 128-byte output line and go to the same warpgroup back to back, pairs alternate between the
+// warpgroups; with an odd number of pairs the last pair is split so that both warpgroups get the same load.
+__device__ __forceinline__ int epi_group(int G, int wg, int k) {
+  const int P = G >> 1;             // full pairs
+  const int Pe = P & ~1;            // pairs that are dealt out two by two
+  const int pairs_mine = Pe >> 1;   // per warpgroup
+  if (k < 2 * pairs_mine) return ((k >> 1) * 2 + wg) * 2 + (k & 1);
+  int kk = k - 2 * pairs_mine;
+  if (P & 1) {                      // split the last pair
+    if (kk == 0) return 2 * Pe + wg;
+    --kk;
+  }
+  if ((G & 1) && kk == 0 && wg == ((P & 1) ? 1 : 0)) return G - 1;   // leftover single group
+  return -1;
+}
+
 // Phase B of the epilogue: the warp walks its 32 staged rows (32 fp32 columns = 8 chunks of 16 bytes per row,
 // 4 rows per instruction) so that every residual load / output store covers a contiguous 64-byte (fp16) or
 // 128-byte (fp32) row segment.  The first residual was prefetched into registers before the accumulator was
@@ -272,14 +289,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         okr[i] = __shfl_sync(0xffffffffu, valid_own, row) != 0;
       }
       // The first residual is prefetched into registers one column group ahead (group 0 while the MMAs of the
-      // tile still run).  Group order per warpgroup: {2wg, 2wg+1, 4+2wg, 4+2wg+1}: both 64-byte halves of an
-      // output line are written back to back by the same warp.
+      // tile still run).  Group schedule: see epi_group().
       uint2 rpre[2][8];
       const uint16_t* r1p = reinterpret_cast<const uint16_t*>(p.res1);
+      const int G = tile_out_cols >> 5;
       auto prefetch_res = [&](int k, uint2 (&dst)[8]) {
-        const int c0 = ((k >> 1) * 4 + wg * 2 + (k & 1)) * 32;
+        const int g = epi_group(G, wg, k);
+        const int c0 = g * 32;
         const int n = n_out_base + c0 + (lane & 7) * 4;
-        const bool n_ok = (c0 < tile_out_cols) && (n + 4 <= n_out_total);
+        const bool n_ok = (g >= 0) && (n + 4 <= n_out_total);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           dst[i] = make_uint2(0, 0);
@@ -292,8 +310,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int c0 = ((k >> 1) * 4 + wg * 2 + (k & 1)) * 32;
-        if (c0 >= tile_out_cols) break;
+        const int gidx = epi_group(G, wg, k);
+        if (gidx < 0) break;
+        const int c0 = gidx * 32;
         if (k + 1 < 4) prefetch_res(k + 1, rpre[(k + 1) & 1]);
         // ---------------- phase A
         float f[32];

@@ -170,7 +170,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
     return out
 
 
-ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "2"))   # 2: ping-pong kernel (default), 1: first-generation kernel
+ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "3"))   # 3: two CTAs/SM, two threads per row (default); 2: ping-pong tiles; 1: first generation
 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
