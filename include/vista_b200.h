@@ -104,6 +104,13 @@ int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const void* k, int64
 int b200v_attention_temporal(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                              void* out, int64_t ld_o, int32_t nb, int32_t T, int32_t S, int32_t heads, void* stream);
 
+/* Frame-sharded variant: queries / outputs are the Tq local frames (rows (b*Tq + t)*S + s), keys / values the T
+ * frames of the whole clip whose row blocks start at token kv_frame_tok[b*T + t] of the k / v buffers (the
+ * all-gathered K|V of every rank).  Replaces the same call sites when frames are sharded over GPUs. */
+int b200v_attention_temporal_sharded(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                                     void* out, int64_t ld_o, int32_t nb, int32_t Tq, int32_t T, int32_t S, int32_t heads,
+                                     const int64_t* kv_frame_tok, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (32 groups) in two phases, fp32 partials / fp64 reduction, bit-reproducible:
  *   stats: per (frame, chunk of b200v_groupnorm_chunk() tokens, group) partial sums go to `partials`
@@ -122,6 +129,15 @@ int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames, int32_t to
 int b200v_groupnorm_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t frames, int32_t tokens_per_frame,
                           int32_t C, int32_t groups, int32_t frames_per_stat, const float* mean_rstd, const float* gamma,
                           const float* beta, int32_t silu, void* stream);
+
+/* Frame-sharded mode (one clip spread over several GPUs): the temporal statistic spans frames held by other
+ * ranks, so `b200v_groupnorm_sums` stops after the local fixed-order reduction and returns raw
+ * sums[stat, group, {sum, sumsq}] (fp64); the caller adds the ranks' sums (NCCL) and calls
+ * `b200v_groupnorm_finalize` with the global element count. */
+int b200v_groupnorm_sums(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C, int32_t groups,
+                         int32_t frames_per_stat, double* partials, int32_t* counters, double* sums, void* stream);
+int b200v_groupnorm_finalize(const double* sums, int32_t n_stat_groups, double count, float eps, float* mean_rstd,
+                             void* stream);
 
 /* LayerNorm over C per token (eps 1e-5), optional fp32 row-vector added to the input first:
  *   y = LN(x + addvec[(token/av_div)%av_mod, :]).   nn.LayerNorm at attention.py:488-490,

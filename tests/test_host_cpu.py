@@ -184,7 +184,7 @@ def test_kernel_register_budgets_fit_their_launch_shape():
                 m = re.search(r"REG:(\d+)", lines[i + 1])
                 assert m, lines[i + 1]
                 regs = int(m.group(1))
-                per_warp = -(-regs * 32 // 512) * 512
+                per_warp = -(-regs * 32 // 256) * 256            # register allocation unit: 256 per warp
                 warps = -(-(threads // 32) // 4) * 4          # warps are allocated in groups of 4 (one per SM sub-partition)
                 assert per_warp * warps <= 65536, (name, regs, threads)
                 found += 1

@@ -356,7 +356,7 @@ extern "C" int b200v_attention_spatial_v2(const void* q, int64_t ld_q, const voi
 namespace vb {
 
 #ifndef VB_ATTN3_POLY_OF_8
-#define VB_ATTN3_POLY_OF_8 3   // of every 8 exponentials, this many use exp2_poly (FMA pipe) instead of MUFU
+#define VB_ATTN3_POLY_OF_8 0   // of every 8 exponentials, this many use exp2_poly (FMA pipe) instead of MUFU
 #endif
 
 template <int POLY8>

@@ -45,7 +45,7 @@ template <int JT>
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_frame, int C, int groups,
                 int frames_per_stat, int chunk, int L, int J, float eps, double* __restrict__ partials,
-                int* __restrict__ counters, float* __restrict__ mean_rstd) {
+                int* __restrict__ counters, float* __restrict__ mean_rstd, double* __restrict__ raw_out) {
   extern __shared__ float sh[];  // [rows][2*C]
   __shared__ int s_last;
   const int frame = blockIdx.y;
@@ -133,11 +133,16 @@ gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_fram
       a += __ldcg(src + (long long)i * groups * 2);
       b += __ldcg(src + (long long)i * groups * 2 + 1);
     }
-    const double mean = a / cnt;
-    double var = b / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mean_rstd[((long long)stat * groups + g) * 2] = (float)mean;
-    mean_rstd[((long long)stat * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    if (raw_out) {   // frame-sharded mode: the caller reduces the sums across ranks and finalises
+      raw_out[((long long)stat * groups + g) * 2] = a;
+      raw_out[((long long)stat * groups + g) * 2 + 1] = b;
+    } else {
+      const double mean = a / cnt;
+      double var = b / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mean_rstd[((long long)stat * groups + g) * 2] = (float)mean;
+      mean_rstd[((long long)stat * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
   if (threadIdx.x == 0) counters[stat] = 0;  // ready for the next launch
 }
@@ -307,7 +312,7 @@ constexpr int kTaWarps = 4;
 __global__ void __launch_bounds__(kTaWarps * 32)
 attn_temporal_kernel(const __half* __restrict__ q, long long ld_q, const __half* __restrict__ k, long long ld_k,
                      const __half* __restrict__ v, long long ld_v, __half* __restrict__ out, long long ld_o, int nb,
-                     int T, int S, int heads) {
+                     int Tq, int T, int S, int heads, const long long* __restrict__ kv_frame_tok) {
   __shared__ __align__(128) uint8_t tiles[kTaWarps][3][32 * 128];   // per warp: Q, K, V tiles of 32 rows x 128 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sQ = smem_u32(tiles[warp][0]), sK = smem_u32(tiles[warp][1]), sV = smem_u32(tiles[warp][2]);
@@ -321,15 +326,19 @@ attn_temporal_kernel(const __half* __restrict__ q, long long ld_q, const __half*
     const long long ps = item / heads;
     const int s = (int)(ps % S);
     const int b = (int)(ps / S);
-    const long long tok0 = (long long)b * T * S + s;
-    // ---- stage q, k, v rows: chunk c (16 B) of row t goes to slot c ^ (t & 7)
+    const long long tok0 = (long long)b * Tq * S + s;   // query / output rows: local frames, clip-major
+    // ---- stage q, k, v rows: chunk c (16 B) of row t goes to slot c ^ (t & 7).  K/V frame t of clip b starts at
+    //      token kv_frame_tok[b*T + t] (frame-sharded mode: gathered from all ranks) or b*T*S + t*S (local).
     for (int i = lane; i < T * 8; i += 32) {
       const int t = i >> 3, c = i & 7;
-      const long long tok = tok0 + (long long)t * S;
+      const long long ktok = (kv_frame_tok ? kv_frame_tok[b * T + t] : ((long long)b * T + t) * S) + s;
       const uint32_t off = t * 128 + ((c ^ (t & 7)) << 4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sQ + off), "l"(q + tok * ld_q + head * 64 + c * 8) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sK + off), "l"(k + tok * ld_k + head * 64 + c * 8) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sV + off), "l"(v + tok * ld_v + head * 64 + c * 8) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sK + off), "l"(k + ktok * ld_k + head * 64 + c * 8) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sV + off), "l"(v + ktok * ld_v + head * 64 + c * 8) : "memory");
+      if (t < Tq) {
+        const long long tok = tok0 + (long long)t * S;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sQ + off), "l"(q + tok * ld_q + head * 64 + c * 8) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -426,7 +435,7 @@ attn_temporal_kernel(const __half* __restrict__ q, long long ld_q, const __half*
       }
     }
     __syncwarp();
-    for (int i = lane; i < T * 8; i += 32) {
+    for (int i = lane; i < Tq * 8; i += 32) {
       const int t = i >> 3, c = i & 7;
       const long long tok = tok0 + (long long)t * S;
       uint4 val;
@@ -708,10 +717,10 @@ static inline int grid_for(long long total, int block, int cap = 148 * 16) {
 
 using namespace vb;
 
-extern "C" int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C,
-                                     int32_t groups, int32_t frames_per_stat, float eps, double* partials,
-                                     int32_t* counters, float* mean_rstd, void* stream) {
-  VB_REQUIRE(x && partials && counters && mean_rstd, "groupnorm_stats: null pointer");
+static int gn_stats_impl(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C, int32_t groups,
+                         int32_t frames_per_stat, float eps, double* partials, int32_t* counters, float* mean_rstd,
+                         double* raw_sums, void* stream) {
+  VB_REQUIRE(x && partials && counters && (mean_rstd || raw_sums), "groupnorm_stats: null pointer");
   VB_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0, "groupnorm_stats: C=%d groups=%d ldx=%lld invalid", C, groups,
              (long long)ldx);
   VB_REQUIRE(frames_per_stat > 0 && frames % frames_per_stat == 0, "groupnorm_stats: frames %% frames_per_stat != 0");
@@ -737,11 +746,47 @@ extern "C" int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames,
 #define VB_GN_STATS(JT)                                                                                              \
   gn_stats_kernel<JT><<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(                                             \
       (const __half*)x, ldx, tokens_per_frame, C, groups, frames_per_stat, chunk, L, J, eps, partials, counters,     \
-      mean_rstd)
+      mean_rstd, raw_sums)
   if (J == 1) VB_GN_STATS(1);
   else if (J == 2) VB_GN_STATS(2);
   else VB_GN_STATS(4);
 #undef VB_GN_STATS
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C,
+                                     int32_t groups, int32_t frames_per_stat, float eps, double* partials,
+                                     int32_t* counters, float* mean_rstd, void* stream) {
+  return gn_stats_impl(x, ldx, frames, tokens_per_frame, C, groups, frames_per_stat, eps, partials, counters, mean_rstd,
+                       nullptr, stream);
+}
+
+extern "C" int b200v_groupnorm_sums(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C,
+                                    int32_t groups, int32_t frames_per_stat, double* partials, int32_t* counters,
+                                    double* sums, void* stream) {
+  return gn_stats_impl(x, ldx, frames, tokens_per_frame, C, groups, frames_per_stat, 0.f, partials, counters, nullptr,
+                       sums, stream);
+}
+
+namespace vb {
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, int n, double count, float eps,
+                                   float* __restrict__ mean_rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = sums[2 * i] / count;
+  double var = sums[2 * i + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_rstd[2 * i] = (float)mean;
+  mean_rstd[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+}  // namespace vb
+
+extern "C" int b200v_groupnorm_finalize(const double* sums, int32_t n_stat_groups, double count, float eps,
+                                        float* mean_rstd, void* stream) {
+  VB_REQUIRE(sums && mean_rstd && n_stat_groups > 0 && count > 0, "groupnorm_finalize: bad args");
+  vb::gn_finalize_kernel<<<(n_stat_groups + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, n_stat_groups, count, eps,
+                                                                                         mean_rstd);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -799,20 +844,35 @@ extern "C" int b200v_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy,
   return 0;
 }
 
-extern "C" int b200v_attention_temporal(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
-                                        int64_t ld_v, void* out, int64_t ld_o, int32_t nb, int32_t T, int32_t S,
-                                        int32_t heads, void* stream) {
+static int attn_temporal_impl(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                              void* out, int64_t ld_o, int32_t nb, int32_t Tq, int32_t T, int32_t S, int32_t heads,
+                              const int64_t* kv_frame_tok, void* stream) {
   VB_REQUIRE(q && k && v && out, "attention_temporal: null pointer");
-  VB_REQUIRE(T >= 1 && T <= 32 && heads >= 1, "attention_temporal: T=%d heads=%d unsupported", T, heads);
+  VB_REQUIRE(T >= 1 && T <= 32 && Tq >= 1 && Tq <= T && heads >= 1, "attention_temporal: T=%d Tq=%d heads=%d unsupported", T,
+             Tq, heads);
   VB_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 8 == 0, "attention_temporal: bad ld");
   const long long items = (long long)nb * S * heads;
   long long blocks = (items + kTaWarps - 1) / kTaWarps;
   const long long cap = (long long)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
   attn_temporal_kernel<<<(unsigned)blocks, kTaWarps * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)q, ld_q, (const __half*)k, ld_k, (const __half*)v, ld_v, (__half*)out, ld_o, nb, T, S, heads);
+      (const __half*)q, ld_q, (const __half*)k, ld_k, (const __half*)v, ld_v, (__half*)out, ld_o, nb, Tq, T, S, heads,
+      reinterpret_cast<const long long*>(kv_frame_tok));
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int b200v_attention_temporal(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
+                                        int64_t ld_v, void* out, int64_t ld_o, int32_t nb, int32_t T, int32_t S,
+                                        int32_t heads, void* stream) {
+  return attn_temporal_impl(q, ld_q, k, ld_k, v, ld_v, out, ld_o, nb, T, T, S, heads, nullptr, stream);
+}
+
+extern "C" int b200v_attention_temporal_sharded(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
+                                                int64_t ld_v, void* out, int64_t ld_o, int32_t nb, int32_t Tq, int32_t T,
+                                                int32_t S, int32_t heads, const int64_t* kv_frame_tok, void* stream) {
+  VB_REQUIRE(kv_frame_tok, "attention_temporal_sharded: null frame table");
+  return attn_temporal_impl(q, ld_q, k, ld_k, v, ld_v, out, ld_o, nb, Tq, T, S, heads, kv_frame_tok, stream);
 }
 
 extern "C" int b200v_conv3x3_small_cin(const void* x, int32_t cin, const float* w, const float* bias, void* out,

@@ -68,6 +68,8 @@ def fused_sample(sampler, den, x: torch.Tensor, cond: Dict, uc: Optional[Dict], 
     N, zc, h, w = x.shape
     assert zc == 4 and N % T == 0
     rt = net._rt_get(net.diffusion_model, T, dev)
+    if getattr(net, "frame_sharded", False):
+        return _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n, T)
     key = (N, h, w)
     states = rt.__dict__.setdefault("_loop_states", {})
     st: _LoopState = states.get(key)
@@ -109,4 +111,41 @@ def fused_sample(sampler, den, x: torch.Tensor, cond: Dict, uc: Optional[Dict], 
         for _ in range(n - 1):
             st.graph.replay()
     x.copy_(st.x)
+    return x
+
+
+def _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n: int, T: int) -> torch.Tensor:
+    """One clip, frames sharded over the ranks (vista_b200/sharded.py).  Every rank receives the same full-clip
+    inputs, advances its own frames and all-gathers the final latent."""
+    from .sharded import gather_latent
+    dev = x.device
+    N, zc, h, w = x.shape
+    assert N == T, "frame-sharded sampling handles one clip"
+    t0, t1 = rt.t0, rt.t1
+    Tl = t1 - t0
+    states = rt.__dict__.setdefault("_loop_states", {})
+    st = states.get((Tl, h, w))
+    if st is None:
+        st = states[(Tl, h, w)] = _LoopState(rt, Tl, h, w)
+    sigmas = sampler.discretization(n, device="cpu").to(torch.float32)
+    x *= torch.sqrt(1.0 + sigmas[0] ** 2).to(dev)
+    st.x.copy_(x[t0:t1])
+    st.sigmas[: n + 1].copy_(sigmas)
+    st.step.zero_()
+    if cond_frame is not None:
+        st.cond_frame.copy_(cond_frame[t0:t1])
+    if cond_mask is not None:
+        st.mask.copy_(cond_mask[t0:t1])
+    else:
+        st.mask.zero_()
+    st.mask2.copy_(torch.cat([st.mask, st.mask]))
+    st.concat_u.copy_(_expand(uc["concat"], N, T)[t0:t1])
+    st.concat_c.copy_(_expand(cond["concat"], N, T)[t0:t1])
+    st.scales.copy_(sampler.guider.scale_vector(T).to(dev, torch.float32)[t0:t1])
+    context = torch.cat((_expand(uc["crossattn"], N, T), _expand(cond["crossattn"], N, T)), 0)
+    y = torch.cat((_expand(uc["vector"], N, T), _expand(cond["vector"], N, T)), 0)
+    rt.set_conditioning(context, y)
+    for _ in range(n):
+        st.one_step(rt, n)
+    x.copy_(gather_latent(st.x, T, group=rt.group))
     return x

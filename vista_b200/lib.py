@@ -98,6 +98,9 @@ SIGNATURES = {
     "b200v_attention_spatial_v3": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_groupnorm_chunk": [],
+    "b200v_groupnorm_sums": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P],
+    "b200v_groupnorm_finalize": [_P, _I32, C.c_double, _F, _P, _P],
+    "b200v_attention_temporal_sharded": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "b200v_groupnorm_stats": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _P],
     "b200v_groupnorm_apply": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P],
     "b200v_layernorm": [_P, _I64, _P, _I64, _I64, _I32, _P, _P, _F, _P, _I64, _I32, _I32, _P],

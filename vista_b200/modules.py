@@ -86,6 +86,15 @@ class _RuntimeOwner:
         self._runtime: Optional[UNetRuntime] = None
         self._runtime_key = None
         self._cond_cache = None
+        self._shard_group = None
+        self.frame_sharded = False
+
+    def enable_frame_sharding(self, group=None):
+        """Spread the frames of ONE clip over the ranks of `group` (BASELINE config 5); see vista_b200/sharded.py.
+        Only the fused sampler drives this mode (every rank passes the same full-clip inputs)."""
+        self.frame_sharded = True
+        self._shard_group = group
+        self._rt_invalidate()
 
     def _rt_invalidate(self):
         self._runtime, self._runtime_key, self._cond_cache = None, None, None
@@ -93,15 +102,21 @@ class _RuntimeOwner:
     def _rt_get(self, model: nn.Module, num_frames: int, device) -> UNetRuntime:
         if not torch.cuda.is_available() or torch.device(device).type != "cuda":
             raise RuntimeError("vista_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
-        key = (num_frames, str(device), id(model))
+        key = (num_frames, str(device), id(model), self.frame_sharded)
         if self._runtime is None or self._runtime_key != key:
             cfg = _infer_config(model)
-            self._runtime = UNetRuntime(cfg, model.state_dict(), device, num_frames)
+            if self.frame_sharded:
+                from .sharded import ShardedUNetRuntime
+                self._runtime = ShardedUNetRuntime(cfg, model.state_dict(), device, num_frames, group=self._shard_group)
+            else:
+                self._runtime = UNetRuntime(cfg, model.state_dict(), device, num_frames)
             self._runtime_key = key
             self._cond_cache = None
         return self._runtime
 
     def _rt_forward(self, model, x, timesteps, context, y, cond_mask, num_frames):
+        if self.frame_sharded:
+            raise RuntimeError("frame-sharded mode is driven by the fused sampler (EulerEDMSampler with a B200Denoiser)")
         rt = self._rt_get(model, num_frames, x.device)
         B, Cin, h, w = x.shape
         if context.shape[0] != B:                                   # video_model.py:463-465

@@ -242,6 +242,44 @@ def groupnorm(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float,
     return y
 
 
+def groupnorm_sums(x, frames: int, tokens_per_frame: int, Cc: int, sums: torch.Tensor, frames_per_stat: int,
+                   groups: int = 32, ws: Optional[GNWorkspace] = None):
+    """Raw per-statistic (sum, sum of squares) in fp64 — first half of the frame-sharded temporal GroupNorm."""
+    l = _lib.load()
+    if ws is None:
+        ws = _default_ws.setdefault(x.device, GNWorkspace(x.device))
+    chunk = l.b200v_groupnorm_chunk()
+    ws.reserve(frames * (-(-tokens_per_frame // chunk)) * groups * 2)
+    _count(1)
+    _lib.check(l.b200v_groupnorm_sums(x.data_ptr(), x.stride(0), frames, tokens_per_frame, Cc, groups, frames_per_stat,
+                                      ws.partials.data_ptr(), ws.counters.data_ptr(), sums.data_ptr(), _stream()),
+               "b200v_groupnorm_sums")
+    return sums
+
+
+def groupnorm_finalize_apply(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float, silu: bool,
+                             sums: torch.Tensor, count: float, stats: torch.Tensor, frames_per_stat: int, groups: int = 32):
+    """Second half: (mean, rstd) from globally reduced sums, then the apply kernel."""
+    l = _lib.load()
+    Cc = gamma.numel()
+    _count(2)
+    _lib.check(l.b200v_groupnorm_finalize(sums.data_ptr(), sums.numel() // 2, float(count), eps, stats.data_ptr(), _stream()),
+               "b200v_groupnorm_finalize")
+    _lib.check(l.b200v_groupnorm_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), frames, tokens_per_frame, Cc,
+                                       groups, frames_per_stat, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                       int(silu), _stream()), "b200v_groupnorm_apply")
+    return y
+
+
+def attention_temporal_sharded(q, k, v, out, nb: int, Tq: int, T: int, S: int, heads: int, kv_frame_tok: torch.Tensor):
+    _count(1)
+    _lib.check(_lib.load().b200v_attention_temporal_sharded(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+                                                            v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
+                                                            nb, Tq, T, S, heads, kv_frame_tok.data_ptr(), _stream()),
+               "b200v_attention_temporal_sharded")
+    return out
+
+
 def layernorm(x, y, gamma, beta, eps: float = 1e-5, addvec=None, av_div: int = 1, av_mod: int = 1):
     tokens, ldx = _rows(x)
     _count(1)

@@ -153,6 +153,13 @@ class UNetRuntime:
         return ops.gemm(a, lin.w, out, bias=lin.b, tile_n=lin.tile_n, act=2 if lin.geglu else kw.pop("act", 0), **kw)
 
     def _gn(self, x, y, B, hw, norm, eps, silu, idx, fps=1):
+        if fps != 1:
+            return self._gn_temporal(x, y, B, hw, norm, eps, silu, idx, fps)
+        return ops.groupnorm(x, y, B, hw, norm[0], norm[1], eps, silu, self.gn_stats[idx, : B // fps],
+                             frames_per_stat=fps, groups=self.cfg.num_groups, ws=self.gn_ws)
+
+    def _gn_temporal(self, x, y, B, hw, norm, eps, silu, idx, fps):
+        """GroupNorm whose statistic spans the frames of a clip (video_model.py:67-72)."""
         return ops.groupnorm(x, y, B, hw, norm[0], norm[1], eps, silu, self.gn_stats[idx, : B // fps],
                              frames_per_stat=fps, groups=self.cfg.num_groups, ws=self.gn_ws)
 
@@ -216,12 +223,19 @@ class UNetRuntime:
         xsp = self.gemm(a2, L["conv2"], self.buf("rb.xsp", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, B), res1=xs)
         # temporal ResBlock: GroupNorm over (C/32, T, H, W), (3,1,1) conv over frames, AlphaBlender
         a3 = self._gn(xsp, self.buf("rb.a1", M, rb.cout), B, hw, L["tgn1"], 1e-5, True, gi + 2, fps=T)
-        h2 = self.gemm(a3, L["tconv1"], self.buf("rb.h1", M, rb.cout), taps=ops.TAPS_T3, geom=(hw, T, nb),
-                       rowvec=self.emb_out[:, L["embt_off"]:L["embt_off"] + rb.cout], rv_div=hw, rv_mod=B)
+        h2 = self._tconv(a3, L["tconv1"], self.buf("rb.h1", M, rb.cout), hw, nb,
+                         rowvec=self.emb_out[:, L["embt_off"]:L["embt_off"] + rb.cout], rv_div=hw, rv_mod=B)
         a4 = self._gn(h2, self.buf("rb.a2", M, rb.cout), B, hw, L["tgn2"], 1e-5, True, gi + 3, fps=T)
         # out = alpha*xsp + (1-alpha)*(xsp + conv) = xsp + (1-alpha)*(conv + bias)      (util.py:317)
-        self.gemm(a4, L["tconv2"], dst, taps=ops.TAPS_T3, geom=(hw, T, nb), s_acc=1.0 - L["alpha"], res1=xsp)
+        self._tconv(a4, L["tconv2"], dst, hw, nb, s_acc=1.0 - L["alpha"], res1=xsp)
         return dst
+
+    def _tconv(self, a, lin: Lin, out, hw: int, nb: int, **epi):
+        """(3,1,1) convolution over the frames of each clip (zero padded at the clip ends)."""
+        return self.gemm(a, lin, out, taps=ops.TAPS_T3, geom=(hw, self.T, nb), **epi)
+
+    def _attn_temporal(self, qkv, o, nb: int, hw: int, heads: int, Cc: int):
+        return ops.attention_temporal(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], o, nb, self.T, hw, heads)
 
     def _svt(self, L, x, dst, B, h, w):
         t: SVTSpec = L["spec"]
@@ -246,7 +260,7 @@ class UNetRuntime:
         u1 = self.gemm(g, L["ffin2"], self.buf("tr.u1", M, Cc), res1=t2, rowvec=pos, rv_div=hw, rv_mod=T)
         n = self._ln(u1, self.buf("tr.n", M, Cc), L["tln1"])
         qkv = self.gemm(n, L["tqkv"], self.buf("tr.qkv", M, 3 * Cc))
-        ops.attention_temporal(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], o, nb, T, hw, t.heads)
+        self._attn_temporal(qkv, o, nb, hw, t.heads, Cc)
         u2 = self.gemm(o, L["tout"], self.buf("tr.t1", M, Cc), res1=u1, rowvec=self.cond["tm"][p], rv_div=T * hw, rv_mod=nb)
         n = self._ln(u2, self.buf("tr.n", M, Cc), L["tln3"])
         g = self.gemm(n, L["tff1"], self.buf("tr.g", M, 4 * Cc))
