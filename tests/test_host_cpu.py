@@ -189,3 +189,26 @@ def test_kernel_register_budgets_fit_their_launch_shape():
                 assert per_warp * warps <= 65536, (name, regs, threads)
                 found += 1
     assert found >= 7
+
+
+def test_engine_from_yaml_config_exposes_reference_state_dict_keys():
+    """configs/inference/vista_b200.yaml instantiates through the reference's own `target:` mechanism and its
+    state_dict carries the checkpoint key names of SURVEY.md Appendix D (model.diffusion_model.*, first_stage_model.decoder.*)."""
+    import yaml
+    from vista_b200.diffusion import instantiate_from_config
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "inference", "vista_b200.yaml")))["model"]
+    p = cfg["params"]
+    p["network_config"]["params"].update(model_channels=64, channel_mult=[1, 2], num_res_blocks=1, attention_resolutions=[1, 2])
+    p["first_stage_config"]["params"]["decoder_config"]["params"].update(ch=64, ch_mult=[1, 2], num_res_blocks=1)
+    eng = instantiate_from_config(cfg)
+    keys = set(eng.state_dict())
+    unet_keys = {"model.diffusion_model." + k for k in spec.unet_param_specs(spec.unet_preset("tiny"))}
+    dec_keys = {"first_stage_model.decoder." + k for k in spec.decoder_param_specs(spec.decoder_preset("tiny"))}
+    assert keys == unet_keys | dec_keys
+    assert eng.scale_factor == 0.18215 and eng.en_and_decode_n_samples_a_time == 14
+    with eng.ema_scope("x"):
+        pass
+    with pytest.raises(NotImplementedError):
+        eng.encode_first_stage(torch.zeros(1, 3, 8, 8))
+    from vista_b200.diffusion import EulerEDMSampler, VanillaCFG
+    assert isinstance(eng.sampler, EulerEDMSampler) and isinstance(eng.sampler.guider, VanillaCFG)

@@ -120,3 +120,40 @@ def test_full_size_edm_step_vs_reference_golden():
           f"ref absmean {float(ref.abs().mean()):.3f}")
     assert torch.isfinite(out).all()
     assert r < 5e-3, r
+
+
+def test_engine_sample_then_decode_vs_oracle():
+    """Whole hot path through the DiffusionEngine surface (sample() -> decode_first_stage()) against the CPU oracle:
+    3-step CFG sample of a tiny network, then the chunked temporal-VAE decode of the 25 latents."""
+    import yaml, os
+    from oracle import vista_oracle as vo
+    from vista_b200.diffusion import instantiate_from_config
+    from helpers import decoder_weights
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, "configs", "inference", "vista_b200.yaml")))["model"]
+    p = cfg["params"]
+    p["network_config"]["params"].update(model_channels=64, channel_mult=[1, 2], num_res_blocks=1, attention_resolutions=[1, 2])
+    p["first_stage_config"]["params"]["decoder_config"]["params"].update(ch=64, ch_mult=[1, 2], num_res_blocks=1)
+    p["sampler_config"]["params"]["num_steps"] = 3
+    p["replace_cond_frames"], p["fixed_cond_frames"] = True, [0]
+    ucfg, usd = unet_weights("tiny")
+    dcfg, dsd = decoder_weights("tiny")
+    with torch.device(DEV):
+        eng = instantiate_from_config(cfg)
+    sd = {"model.diffusion_model." + k: torch.from_numpy(v) for k, v in usd.items()}
+    sd.update({"first_stage_model.decoder." + k: torch.from_numpy(v) for k, v in dsd.items()})
+    missing, unexpected = eng.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    T, h, w = 25, 8, 16
+    c, uc, noise, z, mask = inputs(ucfg, T, h, w, 1)
+    lat = eng.sample(c, cond_frame=z, uc=uc, N=T, shape=(4, h, w), noise=noise)
+    frames = eng.decode_first_stage(lat)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        cpu = lambda d: {k: v.cpu() for k, v in d.items()}
+        lat_ref = vo.euler_edm_sample(to_t(usd), ucfg, noise.cpu(), cpu(c), cpu(uc), z.cpu(), mask.cpu(), 3, T)
+        frames_ref = vo.decode_first_stage(to_t(dsd), dcfg, lat_ref)
+    r1, r2 = rel_l2(lat.cpu(), lat_ref), rel_l2(frames.cpu(), frames_ref)
+    print(f"engine: latent rel-L2 {r1:.3e}, decoded frames rel-L2 {r2:.3e} (frames absmean {float(frames_ref.abs().mean()):.3f})")
+    assert frames.shape == (T, 3, 2 * h, 2 * w)
+    assert r1 < 5e-3 and r2 < 1e-2

@@ -1,0 +1,93 @@
+"""``DiffusionEngine`` surface (vwm/models/diffusion.py:20-131,150-180,306-329) for the hot path: the attributes
+and methods ``sample_utils`` uses (.model, .denoiser, .first_stage_model, .scale_factor, .decode_first_stage,
+.sample, .ema_scope) on top of the B200 executors.  Training, the conditioner and the VAE encoder are out of
+scope: ``encode_first_stage`` / ``conditioner`` raise instead of silently doing something else."""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from .diffusion import B200Denoiser, get_obj_from_str, instantiate_from_config
+from .modules import B200Wrapper
+from .vae import VideoDecoder, decode_first_stage as _decode_first_stage
+
+
+class FirstStage(nn.Module):
+    """Holds the decoder under the reference's key prefix ``first_stage_model.decoder.*``
+    (AutoencodingEngine.decode, vwm/models/autoencoder.py:206-208)."""
+
+    def __init__(self, decoder_config: Dict, **ignored):
+        super().__init__()
+        self.decoder = instantiate_from_config(decoder_config)
+
+    def decode(self, z: torch.Tensor, **kwargs) -> torch.Tensor:
+        return self.decoder(z, **kwargs)
+
+    def encode(self, x, **kwargs):
+        raise NotImplementedError("the VAE encoder runs once per sample and is outside the B200 hot path (SURVEY.md §8f)")
+
+
+class DiffusionEngine(nn.Module):
+    def __init__(self, network_config: Dict, denoiser_config: Dict, first_stage_config: Optional[Dict] = None,
+                 conditioner_config=None, sampler_config: Optional[Dict] = None, scale_factor: float = 1.0,
+                 disable_first_stage_autocast: bool = False, en_and_decode_n_samples_a_time: Optional[int] = None,
+                 num_frames: int = 25, network_wrapper: Optional[str] = None, replace_cond_frames: bool = False,
+                 fixed_cond_frames: Optional[List[int]] = None, input_key: str = "img_seq", **ignored):
+        super().__init__()
+        model = instantiate_from_config(network_config)
+        wrapper = get_obj_from_str(network_wrapper) if network_wrapper else B200Wrapper
+        self.model = wrapper(model, compile_model=False)
+        self.denoiser = instantiate_from_config(denoiser_config)
+        self.sampler = instantiate_from_config(sampler_config) if sampler_config is not None else None
+        if first_stage_config is not None:
+            params = first_stage_config.get("params", first_stage_config)
+            self.first_stage_model = FirstStage(params["decoder_config"])
+        else:
+            self.first_stage_model = None
+        self.scale_factor = scale_factor
+        self.disable_first_stage_autocast = disable_first_stage_autocast
+        self.en_and_decode_n_samples_a_time = en_and_decode_n_samples_a_time
+        self.num_frames = num_frames
+        self.replace_cond_frames = replace_cond_frames
+        self.fixed_cond_frames = fixed_cond_frames
+        self.input_key = input_key
+        self.use_ema = False
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def conditioner(self):
+        raise NotImplementedError("the conditioner (CLIP / VAE-encoder / sinusoids) is outside the hot path; pass c / uc dicts")
+
+    @contextlib.contextmanager
+    def ema_scope(self, context=None):          # no-op at inference (diffusion.py:241-255, use_ema False)
+        yield None
+
+    @torch.no_grad()
+    def decode_first_stage(self, z: torch.Tensor, overlap: int = 3) -> torch.Tensor:
+        dec = self.first_stage_model.decoder
+        if not isinstance(dec, VideoDecoder):
+            raise NotImplementedError("decode_first_stage needs vista_b200.vae.VideoDecoder as decoder_config.target")
+        return _decode_first_stage(dec.runtime(z.device), z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap)
+
+    def encode_first_stage(self, x):
+        raise NotImplementedError("the VAE encoder is outside the B200 hot path (SURVEY.md §8f)")
+
+    @torch.no_grad()
+    def sample(self, cond: Dict, cond_frame=None, uc: Union[Dict, None] = None, N: int = 25,
+               shape: Union[None, Tuple, List] = None, noise: Optional[torch.Tensor] = None, **kwargs):
+        """diffusion.py:306-329; ``noise`` may be injected (device RNG is not reproducible across devices)."""
+        randn = torch.randn(N, *shape).to(self.device) if noise is None else noise.to(self.device).clone()
+        cond_mask = torch.zeros(N).to(self.device)
+        if self.replace_cond_frames:
+            assert self.fixed_cond_frames
+            cond_mask = cond_mask.reshape(-1, self.num_frames)
+            cond_mask[:, self.fixed_cond_frames] = 1
+            cond_mask = cond_mask.reshape(-1)
+        denoiser = B200Denoiser(self.denoiser, self.model)
+        return self.sampler(denoiser, randn, cond, uc=uc, cond_frame=cond_frame, cond_mask=cond_mask)
