@@ -19,6 +19,7 @@ struct TGParams {
   int a_mode;
   int W, H, NB;
   int BW, BH, BB;
+  int bw_sh, bh_sh;             // log2(BW), log2(BH): the box extents are powers of two (product 128)
   int tiles_w, tiles_h;
   int m_tiles, n_tiles;
   int ntaps, kc_per_tap;
@@ -28,17 +29,17 @@ struct TGParams {
   int nstages, stage_bytes;
   long long tokens;
   void* out;
-  long long ldo;
+  int ldo_b;                    // row strides in BYTES (int: one IMAD.WIDE per address)
   int out_f32, act;
   const float* bias;
   const float* rowvec;
-  long long ld_rowvec;
+  int ld_rowvec_b;
   int rv_div, rv_mod;
   const void* res1;
-  long long ld_res1;
+  int ld_res1_b;
   float s_res1;
   const void* res2;
-  long long ld_res2;
+  int ld_res2_b;
   float s_res2;
   float s_acc;
 };
@@ -103,49 +104,8 @@ __device__ __forceinline__ int epi_group(int G, int wg, int k) {
   return -1;
 }
 
-// Phase B of the epilogue: the warp walks its 32 staged rows (32 fp32 columns = 8 chunks of 16 bytes per row,
-// 4 rows per instruction) so that every residual load / output store covers a contiguous 64-byte (fp16) or
-// 128-byte (fp32) row segment.  The first residual was prefetched into registers before the accumulator was
-// ready (u1); a second residual (AlphaBlender GEMMs only) is loaded here, batched ahead of its use.
-__device__ __forceinline__ void epilogue_phase_b(const TGParams& p, uint32_t stg, int lane, const int (&tok)[8],
-                                                 const bool (&okr)[8], const uint2 (&u1)[8], int n, bool n_ok) {
-  const int ch = lane & 7;
-  const int rsub = lane >> 3;
-  const uint16_t* r2p = reinterpret_cast<const uint16_t*>(p.res2);
-  float4 v[8];
-  uint2 u2[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = i * 4 + rsub;
-    const int slot = (ch ^ row) & 7;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
-                 : "r"(stg + row * 128 + slot * 16));
-    u2[i] = make_uint2(0, 0);
-    if (r2p && okr[i] && n_ok) u2[i] = __ldg(reinterpret_cast<const uint2*>(r2p + (long long)tok[i] * p.ld_res2 + n));
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (!(okr[i] && n_ok)) continue;
-    float4 o = v[i];
-    if (p.res1) {
-      const float2 a = unpack2(u1[i].x, p.bf16), b = unpack2(u1[i].y, p.bf16);
-      o.x += p.s_res1 * a.x; o.y += p.s_res1 * a.y; o.z += p.s_res1 * b.x; o.w += p.s_res1 * b.y;
-    }
-    if (r2p) {
-      const float2 a = unpack2(u2[i].x, p.bf16), b = unpack2(u2[i].y, p.bf16);
-      o.x += p.s_res2 * a.x; o.y += p.s_res2 * a.y; o.z += p.s_res2 * b.x; o.w += p.s_res2 * b.y;
-    }
-    if (p.out_f32) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)tok[i] * p.ldo + n) = o;
-    } else {
-      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)tok[i] * p.ldo + n) =
-          make_uint2(pack2(o.x, o.y, p.bf16), pack2(o.z, o.w, p.bf16));
-    }
-  }
-}
-
 // 10 warps are allocated as 12 (granularity 4): 65536 / 384 -> at most 168 registers per thread
+template <int ACT_, bool RV_, int NRES_, bool GEN>
 __global__ void __launch_bounds__(320, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -250,58 +210,74 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 0..7)
-    // Warp w owns TMEM lane quadrant w % 4 (rows 32*(w%4) ..) and every second 32-column group (w / 4).
-    // Phase A: thread = tile row: accumulator -> (+bias)*s_acc + rowvec -> act / GEGLU, fp32, written to the
-    //          warp's staging buffer (32 rows x 32 cols, 16-byte chunks XOR-swizzled by row).
-    // Phase B: coalesced residual loads / output stores (epilogue_phase_b).
+    // Warp w owns TMEM lane quadrant w % 4 (rows 32*(w%4) ..) and the 32-column groups epi_group(G, w/4, .).
+    // Phase A (thread = tile row): tcgen05.ld of the group; GEGLU is evaluated here ((a+ba)*gelu(g+bg)), all other
+    //          epilogues move the raw accumulator; 32 fp32 per row go to the warp's staging buffer (16-byte
+    //          chunks XOR-swizzled by row).
+    // Phase B (lane = 4 fixed columns, 4 rows per instruction): bias / s_acc / row-vector / SiLU / residuals /
+    //          pack / store; per-column operands are loaded once per group, every global access covers a
+    //          contiguous 64-byte (16-bit) or 128-byte (fp32) row segment.  The first residual is prefetched one
+    //          group ahead (group 0 while the MMAs of the tile still run).
+    const int act = GEN ? p.act : ACT_;
+    const bool has_rv = GEN ? (p.rowvec != nullptr) : RV_;
+    const bool has_r1 = GEN ? (p.res1 != nullptr) : (NRES_ >= 1);
+    const bool has_r2 = GEN ? (p.res2 != nullptr) : (NRES_ >= 2);
+    const bool bf16 = GEN ? (p.bf16 != 0) : false;
+    const bool f32o = GEN ? (p.out_f32 != 0) : false;
     int as = 0;
     uint32_t aphase = 0;
     const int quad = warp & 3, wg = warp >> 2;
     const int r = quad * 32 + lane;  // row of the tile == TMEM lane
+    const int ch = lane & 7, rsub = lane >> 3;
     const uint32_t stg = smem_u32(stages + p.nstages * p.stage_bytes) + warp * (32 * 128);
     const int half = p.TN >> 1;
-    const int tile_out_cols = (p.act == 2) ? half : p.TN;
-    const int n_out_total = (p.act == 2) ? (p.N >> 1) : p.N;
+    const int tile_out_cols = (act == 2) ? half : p.TN;
+    const int n_out_total = (act == 2) ? (p.N >> 1) : p.N;
+    const int G = tile_out_cols >> 5;
+    const int out_es = f32o ? 4 : 2;
+    const char* r1p = reinterpret_cast<const char*>(p.res1);
+    const char* r2p = reinterpret_cast<const char*>(p.res2);
+    const bool has_bias = p.bias != nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
       int token_own, valid_own;
       if (p.a_mode == 0) {
         token_own = m_blk * 128 + r;
         valid_own = token_own < p.tokens;
       } else {
         const int tw = m_blk % p.tiles_w;
-        const int th = (m_blk / p.tiles_w) % p.tiles_h;
-        const int tb = m_blk / (p.tiles_w * p.tiles_h);
-        const int ww = r % p.BW, hh = (r / p.BW) % p.BH, bb = r / (p.BW * p.BH);
+        const int t2 = m_blk / p.tiles_w;
+        const int th = t2 % p.tiles_h;
+        const int tb = t2 / p.tiles_h;
+        const int ww = r & (p.BW - 1), hh = (r >> p.bw_sh) & (p.BH - 1), bb = r >> (p.bw_sh + p.bh_sh);
         const int w = tw * p.BW + ww, h = th * p.BH + hh, b = tb * p.BB + bb;
         valid_own = (w < p.W) && (h < p.H) && (b < p.NB);
         token_own = (b * p.H + h) * p.W + w;
       }
-      const float* rv_ptr = p.rowvec ? p.rowvec + (long long)((token_own / p.rv_div) % p.rv_mod) * p.ld_rowvec : nullptr;
-      const int n_out_base = n_blk * tile_out_cols;
-      // rows this lane serves in phase B (4 rows per instruction, 8 instructions) and their tokens
-      int tok[8];
-      bool okr[8];
+      if (!valid_own) token_own = 0;
+      // rows this lane serves in phase B: row(i) = 4 i + rsub
+      const uint32_t vrows = __ballot_sync(0xffffffffu, valid_own) >> rsub;   // bit 4 i <-> row(i)
+      int tok[8], rvrow[8];
+      {
+        const int rv_own = has_rv ? (token_own / p.rv_div) % p.rv_mod : 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = i * 4 + (lane >> 3);
-        tok[i] = __shfl_sync(0xffffffffu, token_own, row);
-        okr[i] = __shfl_sync(0xffffffffu, valid_own, row) != 0;
+        for (int i = 0; i < 8; ++i) {
+          tok[i] = __shfl_sync(0xffffffffu, token_own, i * 4 + rsub);
+          rvrow[i] = has_rv ? __shfl_sync(0xffffffffu, rv_own, i * 4 + rsub) : 0;
+        }
       }
-      // The first residual is prefetched into registers one column group ahead (group 0 while the MMAs of the
-      // tile still run).  Group schedule: see epi_group().
+      const int n_out_base = n_blk * tile_out_cols;
       uint2 rpre[2][8];
-      const uint16_t* r1p = reinterpret_cast<const uint16_t*>(p.res1);
-      const int G = tile_out_cols >> 5;
       auto prefetch_res = [&](int k, uint2 (&dst)[8]) {
+        if (!has_r1) return;
         const int g = epi_group(G, wg, k);
-        const int c0 = g * 32;
-        const int n = n_out_base + c0 + (lane & 7) * 4;
-        const bool n_ok = (g >= 0) && (n + 4 <= n_out_total);
+        const int n = n_out_base + g * 32 + ch * 4;
+        const bool ok = (g >= 0) && (n + 4 <= n_out_total);
+        const char* base = r1p + (long long)n * 2;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           dst[i] = make_uint2(0, 0);
-          if (r1p && n_ok && okr[i]) dst[i] = __ldg(reinterpret_cast<const uint2*>(r1p + (long long)tok[i] * p.ld_res1 + n));
+          if (ok && ((vrows >> (4 * i)) & 1u)) dst[i] = __ldg(reinterpret_cast<const uint2*>(base + (long long)tok[i] * p.ld_res1_b));
         }
       };
       prefetch_res(0, rpre[0]);
@@ -315,26 +291,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c0 = gidx * 32;
         if (k + 1 < 4) prefetch_res(k + 1, rpre[(k + 1) & 1]);
         // ---------------- phase A
-        float f[32];
-        if (p.act != 2) {
+        if (act != 2) {
           uint32_t v[32];
           tmem_ld32(t_row + c0, v);
           tmem_ld_wait();
-          const int n0 = n_out_base + c0;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool in = n0 + g * 4 + 4 <= p.N;
-            if (p.bias && in) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
-            if (rv_ptr && in) rv = __ldg(reinterpret_cast<const float4*>(rv_ptr + n0 + g * 4));
-            f[g * 4 + 0] = (__uint_as_float(v[g * 4 + 0]) + bv.x) * p.s_acc + rv.x;
-            f[g * 4 + 1] = (__uint_as_float(v[g * 4 + 1]) + bv.y) * p.s_acc + rv.y;
-            f[g * 4 + 2] = (__uint_as_float(v[g * 4 + 2]) + bv.z) * p.s_acc + rv.z;
-            f[g * 4 + 3] = (__uint_as_float(v[g * 4 + 3]) + bv.w) * p.s_acc + rv.w;
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
+          for (int j = 0; j < 8; ++j) {
+            const int slot = (j ^ lane) & 7;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + slot * 16), "r"(v[j * 4]),
+                         "r"(v[j * 4 + 1]), "r"(v[j * 4 + 2]), "r"(v[j * 4 + 3])
+                         : "memory");
           }
         } else {
           uint32_t va[32], vg[32];
@@ -343,30 +309,87 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
           const int nb = n_blk * p.TN + c0;  // bias index of the value columns (gate: + half)
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int j = 0; j < 8; ++j) {
             float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) {
-              ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
-              bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + half + g * 4));
+            if (has_bias) {
+              ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j * 4));
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + half + j * 4));
             }
-            f[g * 4 + 0] = (__uint_as_float(va[g * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 0]) + bg.x);
-            f[g * 4 + 1] = (__uint_as_float(va[g * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 1]) + bg.y);
-            f[g * 4 + 2] = (__uint_as_float(va[g * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 2]) + bg.z);
-            f[g * 4 + 3] = (__uint_as_float(va[g * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(vg[g * 4 + 3]) + bg.w);
+            const float f0 = (__uint_as_float(va[j * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(vg[j * 4 + 0]) + bg.x);
+            const float f1 = (__uint_as_float(va[j * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(vg[j * 4 + 1]) + bg.y);
+            const float f2 = (__uint_as_float(va[j * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(vg[j * 4 + 2]) + bg.z);
+            const float f3 = (__uint_as_float(va[j * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(vg[j * 4 + 3]) + bg.w);
+            const int slot = (j ^ lane) & 7;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + slot * 16), "f"(f0), "f"(f1),
+                         "f"(f2), "f"(f3)
+                         : "memory");
           }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int slot = (j ^ lane) & 7;
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + slot * 16), "f"(f[j * 4]),
-                       "f"(f[j * 4 + 1]), "f"(f[j * 4 + 2]), "f"(f[j * 4 + 3])
-                       : "memory");
         }
         __syncwarp();
         // ---------------- phase B
         {
-          const int n = n_out_base + c0 + (lane & 7) * 4;
-          epilogue_phase_b(p, stg, lane, tok, okr, rpre[k & 1], n, n + 4 <= n_out_total);
+          const int n = n_out_base + c0 + ch * 4;
+          const bool n_ok = n + 4 <= n_out_total;
+          float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+          float sa = 1.0f;
+          if (act != 2) {
+            sa = p.s_acc;
+            if (has_bias && n_ok) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              bs = make_float4(b4.x * sa, b4.y * sa, b4.z * sa, b4.w * sa);
+            }
+          }
+          char* obase = reinterpret_cast<char*>(p.out) + (long long)n * out_es;
+          const char* r2base = r2p + (long long)n * 2;
+          const char* rvbase = reinterpret_cast<const char*>(p.rowvec) + (long long)n * 4;
+          const uint2(&u1)[8] = rpre[k & 1];
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            float4 v[4], rv[4];
+            uint2 u2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = hb * 4 + q;
+              const int row = i * 4 + rsub;
+              const int slot = (ch ^ row) & 7;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
+                           : "r"(stg + row * 128 + slot * 16));
+              const bool ok = n_ok && ((vrows >> (4 * i)) & 1u);
+              rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+              u2[q] = make_uint2(0, 0);
+              if (has_rv && ok) rv[q] = __ldg(reinterpret_cast<const float4*>(rvbase + (long long)rvrow[i] * p.ld_rowvec_b));
+              if (has_r2 && ok) u2[q] = __ldg(reinterpret_cast<const uint2*>(r2base + (long long)tok[i] * p.ld_res2_b));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = hb * 4 + q;
+              const bool ok = n_ok && ((vrows >> (4 * i)) & 1u);   // straight-line code, predicated store
+              float4 o = v[q];
+              if (act != 2) {
+                o.x = fmaf(o.x, sa, bs.x); o.y = fmaf(o.y, sa, bs.y); o.z = fmaf(o.z, sa, bs.z); o.w = fmaf(o.w, sa, bs.w);
+                if (has_rv) { o.x += rv[q].x; o.y += rv[q].y; o.z += rv[q].z; o.w += rv[q].w; }
+                if (act == 1) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+                if (has_r1) {
+                  const float2 a = unpack2(u1[i].x, bf16), b = unpack2(u1[i].y, bf16);
+                  o.x = fmaf(p.s_res1, a.x, o.x); o.y = fmaf(p.s_res1, a.y, o.y);
+                  o.z = fmaf(p.s_res1, b.x, o.z); o.w = fmaf(p.s_res1, b.y, o.w);
+                }
+                if (has_r2) {
+                  const float2 a = unpack2(u2[q].x, bf16), b = unpack2(u2[q].y, bf16);
+                  o.x = fmaf(p.s_res2, a.x, o.x); o.y = fmaf(p.s_res2, a.y, o.y);
+                  o.z = fmaf(p.s_res2, b.x, o.z); o.w = fmaf(p.s_res2, b.y, o.w);
+                }
+              }
+              char* optr = obase + (long long)tok[i] * p.ldo_b;
+              if (f32o) {
+                if (ok) *reinterpret_cast<float4*>(optr) = o;
+              } else {
+                const uint2 pk = make_uint2(pack2(o.x, o.y, bf16), pack2(o.z, o.w, bf16));
+                if (ok) *reinterpret_cast<uint2*>(optr) = pk;
+              }
+            }
+          }
         }
         __syncwarp();
       }
@@ -463,24 +486,47 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   constexpr int kStagingBytes = 8 * 32 * 128;  // epilogue transpose buffers (8 warps x 32 rows x 32 fp32)
   p.nstages = (227 * 1024 - 2048 - kStagingBytes) / p.stage_bytes;
   if (p.nstages > kMaxStages) p.nstages = kMaxStages;
-  p.out = d->out; p.ldo = d->ldo; p.out_f32 = d->out_f32; p.act = d->act;
+  const long long kMaxLd = (1ll << 31) - 1;
+  VB_REQUIRE(d->ldo * (d->out_f32 ? 4 : 2) <= kMaxLd && d->ld_rowvec * 4 <= kMaxLd && d->ld_res1 * 2 <= kMaxLd &&
+                 d->ld_res2 * 2 <= kMaxLd,
+             "b200v_gemm: row stride too large");
+  for (p.bw_sh = 0; (1 << p.bw_sh) < p.BW; ++p.bw_sh) {}
+  for (p.bh_sh = 0; (1 << p.bh_sh) < p.BH; ++p.bh_sh) {}
+  p.out = d->out; p.ldo_b = (int)(d->ldo * (d->out_f32 ? 4 : 2)); p.out_f32 = d->out_f32; p.act = d->act;
   p.bias = d->bias;
-  p.rowvec = d->rowvec; p.ld_rowvec = d->ld_rowvec; p.rv_div = d->rv_div > 0 ? d->rv_div : 1;
+  p.rowvec = d->rowvec; p.ld_rowvec_b = (int)(d->ld_rowvec * 4); p.rv_div = d->rv_div > 0 ? d->rv_div : 1;
   p.rv_mod = d->rv_mod > 0 ? d->rv_mod : 1;
-  p.res1 = d->res1; p.ld_res1 = d->ld_res1; p.s_res1 = d->s_res1;
-  p.res2 = d->res2; p.ld_res2 = d->ld_res2; p.s_res2 = d->s_res2;
+  p.res1 = d->res1; p.ld_res1_b = (int)(d->ld_res1 * 2); p.s_res1 = d->s_res1;
+  p.res2 = d->res2; p.ld_res2_b = (int)(d->ld_res2 * 2); p.s_res2 = d->s_res2;
   p.s_acc = d->s_acc;
+  VB_REQUIRE(!(d->res2 && !d->res1), "b200v_gemm: res2 without res1");
 
   const int smem_bytes = 1024 + 1024 + p.nstages * p.stage_bytes + kStagingBytes;
+  // Epilogue variant: the common fp16 feature sets are compiled in (no per-element feature tests), everything
+  // else (bf16 operands, fp32 output, unusual combinations) takes the generic instantiation.
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const TGParams);
+  static const Kern kVariants[8] = {
+      tapgemm_kernel<0, false, 0, false>, tapgemm_kernel<0, false, 1, false>, tapgemm_kernel<0, false, 2, false>,
+      tapgemm_kernel<0, true, 0, false>,  tapgemm_kernel<0, true, 1, false>,  tapgemm_kernel<1, false, 0, false>,
+      tapgemm_kernel<2, false, 0, false>, tapgemm_kernel<0, true, 2, true>};
+  int variant = 7;
+  if (!d->bf16 && !d->out_f32 && !getenv("VB_GEMM_GENERIC")) {
+    const int nres = (d->res1 ? 1 : 0) + (d->res2 ? 1 : 0);
+    if (d->act == 0 && !d->rowvec) variant = nres;
+    else if (d->act == 0 && nres <= 1) variant = 3 + nres;
+    else if (d->act == 1 && !d->rowvec && nres == 0) variant = 5;
+    else if (d->act == 2) variant = 6;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 8; ++i)
+      VB_CHECK_CUDA(cudaFuncSetAttribute(kVariants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const long long total = (long long)p.m_tiles * p.n_tiles;
   int grid = device_sm_count();
   if (total < grid) grid = (int)total;
-  tapgemm_kernel<<<grid, 320, smem_bytes, stream>>>(tmA, tmB, p);
+  kVariants[variant]<<<grid, 320, smem_bytes, stream>>>(tmA, tmB, p);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
