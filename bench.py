@@ -171,8 +171,8 @@ def run_ours(args):
     to_dev = lambda d: {k: v.to(dev, non_blocking=True) for k, v in d.items()}
 
     # ---- device-resident timing: K sampler steps bracketed by events.
-    #      N = 1: the step is replayed from a CUDA graph.  N > 1: the frames of the ONE clip are sharded over the ranks
-    #      (K/V all-gather, GN-sum all-reduce, one-frame halos: vista_b200/sharded.py), steps are launched eagerly.
+    #      N = 1: the step is replayed from a CUDA graph.  N > 1: the ONE clip is spread over the ranks: CFG halves
+    #      first (even N), then frames (K/V all-gather, GN-sum all-reduce, one-frame halos: vista_b200/sharded.py).
     c, uc = to_dev(c_h), to_dev(uc_h)
     noise, z, mask = noise_h.to(dev), z_h.to(dev), mask_h.to(dev)
     sharded = world > 1
@@ -189,16 +189,8 @@ def run_ours(args):
     l0 = ops.LAUNCHES
     st.one_step(rt, n_total)   # eager (counts launches of one step)
     launches_per_step = ops.LAUNCHES - l0
-    if sharded:
-        run_step = lambda: st.one_step(rt, n_total)
-        x0 = noise[rt.t0:rt.t1]
-    else:
-        g = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g):
-            st.one_step(rt, n_total)
-        run_step = g.replay
-        x0 = noise
+    run_step = st.runner(rt, n_total)          # CUDA-graph replay unless the UNet itself holds collectives
+    x0 = noise[rt.t0:rt.t1] if sharded else noise
     st.x.copy_(x0 * torch.sqrt(1.0 + sig[0] ** 2).to(dev))
     st.sigmas[: n_total + 1].copy_(sig)
     st.step.zero_()
@@ -268,6 +260,16 @@ def run_ours(args):
         total = 50 * step_seconds + (decode_s or 0.0)
         return T / total          # one clip: N > 1 shards its frames (strong scaling)
 
+    if world == 1:
+        shard_desc = "single GPU"
+    elif net.cfg_half is not None:
+        shard_desc = (f"one clip over {world} GPUs: CFG halves x frames ({world // 2} frame shard(s) per half); per step a "
+                      f"pairwise all-gather of the 4-channel network output" +
+                      ("" if world == 2 else ", and inside each half temporal K/V all-gather, GN-sum all-reduce, 1-frame halos") +
+                      " (NCCL); decode on rank 0")
+    else:
+        shard_desc = (f"frames of one clip over {world} GPUs: temporal K/V all-gather, GN-sum all-reduce, 1-frame halos "
+                      f"(NCCL); decode on rank 0")
     peaks = load_peaks()
     full = args.config == "full"
     ach = (F_STEP_TFLOP / step_s) if full else None
@@ -281,8 +283,7 @@ def run_ours(args):
                    "step": "one EDM/Euler step (prepare + UNet + update); frames/s = 25/(50*step + decode)",
                    "decode": "included" if decode_s is not None else "NOT IMPLEMENTED YET: value is sampler-only",
                    "l2": "activations per step (> 10 GB) exceed the 126 MB L2; no explicit flush",
-                   "sharding": (f"frames of one clip over {world} GPUs: temporal K/V all-gather, GN-sum all-reduce, 1-frame halos "
-                                f"(NCCL); decode on rank 0") if world > 1 else "single GPU"},
+                   "sharding": shard_desc},
         "decode_ms": None if decode_s is None else decode_s * 1e3,
         "finite": finite,
         "gpu_launches": launches_per_step * K,

@@ -113,8 +113,10 @@ int b200v_attention_temporal_sharded(const void* q, int64_t ld_q, const void* k,
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (32 groups) in two phases, fp32 partials / fp64 reduction, bit-reproducible:
- *   stats: per (frame, chunk of b200v_groupnorm_chunk() tokens, group) partial sums go to `partials`
- *          ([frames * chunks * groups * 2] doubles of scratch); the last block of each statistic
+ *   stats: per (frame, chunk of tokens, group) partial sums go to `partials`; the chunk length is chosen per
+ *          shape and is never below b200v_groupnorm_chunk(), so
+ *          frames * ceil(tokens_per_frame / b200v_groupnorm_chunk()) * groups * 2 doubles of scratch always
+ *          suffice; the last block of each statistic
  *          (stat = frame / frames_per_stat, ticket in `counters`, which must be zero on first use and is
  *          left zero) reduces them in a fixed order and writes mean_rstd[stat, group, {mean, rstd}].
  *   apply: y = (x - mean) * rstd * gamma + beta, optional SiLU, fp16 out
@@ -123,6 +125,8 @@ int b200v_attention_temporal_sharded(const void* q, int64_t ld_q, const void* k,
  * (video_model.py:67-72 with openaimodel.py:195-199, dims=3).
  * ---------------------------------------------------------------------------------------------- */
 int b200v_groupnorm_chunk(void);
+/* the chunk length b200v_groupnorm_stats uses for this shape (exact scratch sizing) */
+int b200v_groupnorm_chunk_for(int32_t frames, int32_t tokens_per_frame);
 int b200v_groupnorm_stats(const void* x, int64_t ldx, int32_t frames, int32_t tokens_per_frame, int32_t C,
                           int32_t groups, int32_t frames_per_stat, float eps, double* partials, int32_t* counters,
                           float* mean_rstd, void* stream);

@@ -50,3 +50,44 @@ def test_two_rank_gloo_collectives():
         assert ok_gather
         assert t == 2.0                      # max over ranks
         assert tot == [[3.0, 6.0]]           # 1+2, 2+4: identical on both ranks
+
+
+def _topology_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vista_b200.modules import _RuntimeOwner
+        owner = type("Owner", (_RuntimeOwner,), {})()
+        owner._rt_init()
+        owner.enable_frame_sharding()
+        pair = sorted(dist.get_process_group_ranks(owner.pair_group))
+        frames = sorted(dist.get_process_group_ranks(owner._shard_group))
+        # the pair exchange: lower rank = unconditional half comes first in the gathered buffer
+        mine = torch.full((2,), float(rank))
+        both = torch.empty(4)
+        dist.all_gather_into_tensor(both, mine, group=owner.pair_group)
+        q.put((rank, owner.cfg_half, owner._frame_world, pair, frames, both.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_split_topology_four_ranks():
+    """modules.enable_frame_sharding with an even world: ranks [0, W/2) own the unconditional half, [W/2, W) the
+    conditional half; pair (i, i + W/2) shares frames; the pair all-gather orders the halves (u, c)."""
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_topology_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, half, fw, pair, frames, both in res:
+        assert half == rank // 2 and fw == 2
+        assert pair == [rank % 2, rank % 2 + 2]
+        assert frames == [2 * half, 2 * half + 1]
+        lo, hi = float(pair[0]), float(pair[1])
+        assert both == [lo, lo, hi, hi]

@@ -1,5 +1,6 @@
-"""Frame-sharded sampling (one clip over 2 GPUs, NCCL) must reproduce the single-GPU result and the REAL
-reference's golden sample.  Needs >= 2 CUDA devices (skipped otherwise).  Tolerance: the sharded path only
+"""Sharded sampling (one clip over 2 GPUs, NCCL) must reproduce the single-GPU result and the REAL reference's
+golden sample, in both layouts: frames sharded (K/V all-gather, GN-sum all-reduce, halos) and CFG halves split
+(pairwise exchange of the network output, CUDA-graph replay of the local UNet).  Needs >= 2 CUDA devices (skipped otherwise).  Tolerance: the sharded path only
 re-associates the temporal GroupNorm sums (rank partials), everything else is the same arithmetic; fp16
 rounding noise re-samples, so we require rel-L2 <= 3e-3 between the two and <= 5e-3 against the reference."""
 import os
@@ -40,15 +41,16 @@ def _worker(rank, world, port, q):
         den = Denoiser({"target": "vista_b200.diffusion.VScalingWithEDMcNoise"}, num_frames=T)
         smp = make_sampler(steps)
         res = {}
-        for mode in ("single", "sharded"):
+        for mode in ("single", "frames", "split"):
             net = B200Wrapper(unet)
-            if mode == "sharded":
-                net.enable_frame_sharding()
+            if mode != "single":
+                net.enable_frame_sharding(cfg_split=(mode == "split"))
+                assert (net.cfg_half is not None) == (mode == "split")
             out = smp(B200Denoiser(den, net), torch.from_numpy(noise).to(dev), td(c), uc=td(uc),
                       cond_frame=torch.from_numpy(z).to(dev), cond_mask=torch.from_numpy(mask).to(dev))
             torch.cuda.synchronize()
             res[mode] = out.cpu()
-        q.put((rank, res["single"].numpy(), res["sharded"].numpy()))
+        q.put((rank, res["single"].numpy(), res["frames"].numpy(), res["split"].numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -68,9 +70,13 @@ def test_two_gpu_frame_sharded_sample_matches_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     ref = torch.from_numpy(golden("sampler_tiny_cfg")["sample"])
-    for rank, single, sharded in outs:
-        single, sharded = torch.from_numpy(single), torch.from_numpy(sharded)
-        r1, r2, r3 = rel_l2(sharded, single), rel_l2(sharded, ref), rel_l2(single, ref)
-        print(f"rank {rank}: sharded-vs-single {r1:.3e}, sharded-vs-reference {r2:.3e}, single-vs-reference {r3:.3e}")
-        assert r1 < 3e-3 and r2 < 5e-3
+    for rank, single, frames, split in outs:
+        single = torch.from_numpy(single)
+        print(f"rank {rank}: single-vs-reference {rel_l2(single, ref):.3e}")
+        for name, arr in (("frames", frames), ("split", split)):
+            sharded = torch.from_numpy(arr)
+            r1, r2 = rel_l2(sharded, single), rel_l2(sharded, ref)
+            print(f"rank {rank}: {name}-vs-single {r1:.3e}, {name}-vs-reference {r2:.3e}")
+            assert r1 < 3e-3 and r2 < 5e-3
     assert np.array_equal(outs[0][2], outs[1][2]), "every rank must hold the same gathered latent"
+    assert np.array_equal(outs[0][3], outs[1][3]), "every rank must hold the same latent (CFG split)"

@@ -39,6 +39,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 // floating-point atomics, no memset (the counter resets itself).
 // ------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
+constexpr int kGnMinChunk = 16;   // b200v_groupnorm_chunk(): lower bound of the tokens one block walks
+// Tokens per block: about 8 blocks per SM over the whole launch (small feature maps would otherwise leave most
+// SMs idle), a multiple of 8, within [kGnMinChunk, 256].  A pure function of the shape: results stay
+// bit-reproducible from run to run.
+static inline int gn_pick_chunk(int frames, int tokens_per_frame) {
+  long long c = ((long long)frames * tokens_per_frame + 1183) / 1184;
+  c = (c + 7) / 8 * 8;
+  if (c < kGnMinChunk) c = kGnMinChunk;
+  if (c > 256) c = 256;
+  return (int)c;
+}
 constexpr int kGnMaxJ = 4;  // max vectors per thread (C <= 8 * 256 * kGnMaxJ); kernels are templated on 1 / 2 / 4
 
 template <int JT>
@@ -125,13 +136,28 @@ gn_stats_kernel(const __half* __restrict__ x, long long ldx, int tokens_per_fram
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // Final reduction, fixed order: 8 threads per group each add every 8th partial in index order, thread 0 of the
+  // group adds the 8 sub-sums in order (the partial count reaches frames_per_stat * chunks ~ 10^3).
   const double cnt = (double)cpg * tokens_per_frame * frames_per_stat;
-  for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+  double* red = reinterpret_cast<double*>(sh);   // [groups][8][2]; the row partials in sh are dead by now
+  const int n_part = frames_per_stat * chunks;
+  for (int idx = threadIdx.x; idx < groups * 8; idx += kGnThreads) {
+    const int g = idx >> 3, sub = idx & 7;
     double a = 0.0, b = 0.0;
-    const double* src = partials + ((long long)stat * frames_per_stat * chunks * groups + g) * 2;
-    for (int i = 0; i < frames_per_stat * chunks; ++i) {
+    const double* src = partials + ((long long)stat * n_part * groups + g) * 2;
+    for (int i = sub; i < n_part; i += 8) {
       a += __ldcg(src + (long long)i * groups * 2);
       b += __ldcg(src + (long long)i * groups * 2 + 1);
+    }
+    red[idx * 2] = a;
+    red[idx * 2 + 1] = b;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+    double a = 0.0, b = 0.0;
+    for (int sub = 0; sub < 8; ++sub) {
+      a += red[(g * 8 + sub) * 2];
+      b += red[(g * 8 + sub) * 2 + 1];
     }
     if (raw_out) {   // frame-sharded mode: the caller reduces the sums across ranks and finalises
       raw_out[((long long)stat * groups + g) * 2] = a;
@@ -732,9 +758,10 @@ static int gn_stats_impl(const void* x, int64_t ldx, int32_t frames, int32_t tok
   }
   VB_REQUIRE(J <= kGnMaxJ, "groupnorm_stats: C=%d too large", C);
   const int rows = kGnThreads / L;
-  const int chunk = b200v_groupnorm_chunk();
+  const int chunk = gn_pick_chunk(frames, tokens_per_frame);
   dim3 grid((tokens_per_frame + chunk - 1) / chunk, frames);
-  const size_t smem = (size_t)rows * 2 * C * sizeof(float);
+  size_t smem = (size_t)rows * 2 * C * sizeof(float);
+  if (smem < (size_t)groups * 8 * 2 * sizeof(double)) smem = (size_t)groups * 8 * 2 * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -791,7 +818,10 @@ extern "C" int b200v_groupnorm_finalize(const double* sums, int32_t n_stat_group
   return 0;
 }
 
-extern "C" int b200v_groupnorm_chunk(void) { return 256; }
+extern "C" int b200v_groupnorm_chunk(void) { return vb::kGnMinChunk; }
+extern "C" int b200v_groupnorm_chunk_for(int32_t frames, int32_t tokens_per_frame) {
+  return vb::gn_pick_chunk(frames, tokens_per_frame);
+}
 
 extern "C" int b200v_groupnorm_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t frames,
                                      int32_t tokens_per_frame, int32_t C, int32_t groups, int32_t frames_per_stat,
@@ -807,7 +837,8 @@ extern "C" int b200v_groupnorm_apply(const void* x, int64_t ldx, void* y, int64_
     L = (nvec + J - 1) / J;
   }
   VB_REQUIRE(J <= kGnMaxJ, "groupnorm_apply: C=%d too large", C);
-  const int chunk = 128;
+  int chunk = gn_pick_chunk(frames, tokens_per_frame);
+  if (chunk > 128) chunk = 128;
   dim3 grid((tokens_per_frame + chunk - 1) / chunk, frames);
 #define VB_GN_APPLY(JT)                                                                                              \
   gn_apply_kernel<JT><<<grid, kGnThreads, 0, (cudaStream_t)stream>>>(                                                \

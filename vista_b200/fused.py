@@ -41,14 +41,63 @@ class _LoopState:
         self.unet_in = torch.empty(2 * N * h * w, 8, dtype=torch.float16, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_steps = None
+        # CFG-split mode (modules.enable_frame_sharding): this rank runs one half of the doubled batch
+        self.split = None            # (half, pair process group)
+        self.net_full = None         # [2 N h w, 8] fp32: both halves' network outputs after the pair exchange
+        self._fwd_out = None
+
+    def configure_split(self, half: int, pair_group):
+        self.split = (half, pair_group)
+        if self.net_full is None:
+            self.net_full = torch.empty(2 * self.N * self.h * self.w, 8, dtype=torch.float32, device=self.x.device)
+
+    def _prepare(self):
+        ops.sampler_prepare(self.x, self.cond_frame, self.mask, self.concat_u, self.concat_c, self.sigmas, self.step,
+                            self.unet_in, self.c_noise, self.N, self.h, self.w)
+
+    def _forward(self, rt):
+        N, h, w = self.N, self.h, self.w
+        if self.split is None:
+            return rt.forward(self.unet_in, self.c_noise, self.mask2, h, w)
+        half, rows = self.split[0], N * h * w
+        return rt.forward(self.unet_in[half * rows:(half + 1) * rows], self.c_noise[half * N:(half + 1) * N],
+                          self.mask2[half * N:(half + 1) * N], h, w)
+
+    def _finish(self, net_out, num_steps: int):
+        if self.split is not None:                # guidance needs both halves of the frames this rank owns
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.net_full, net_out, group=self.split[1])
+            net_out = self.net_full
+        ops.sampler_update(self.x, net_out, self.cond_frame, self.mask, self.scales, self.sigmas, self.step,
+                           num_steps, self.N, self.h, self.w)
 
     def one_step(self, rt, num_steps: int):
-        N, h, w = self.N, self.h, self.w
-        ops.sampler_prepare(self.x, self.cond_frame, self.mask, self.concat_u, self.concat_c, self.sigmas, self.step,
-                            self.unet_in, self.c_noise, N, h, w)
-        net_out = rt.forward(self.unet_in, self.c_noise, self.mask2, h, w)
-        ops.sampler_update(self.x, net_out, self.cond_frame, self.mask, self.scales, self.sigmas, self.step,
-                           num_steps, N, h, w)
+        self._prepare()
+        self._finish(self._forward(rt), num_steps)
+
+    def runner(self, rt, num_steps: int):
+        """Callable advancing one step the fastest supported way; call after one eager step (which allocates every
+        buffer of the executor).  Without a collective inside the UNet the launch sequence is replayed from a CUDA
+        graph: the whole step, or prepare + UNet in CFG-split mode (the pair exchange and the update stay eager)."""
+        if not USE_GRAPH or getattr(rt, "group", None) is not None:
+            return lambda: self.one_step(rt, num_steps)
+        if self.graph is None or self.graph_steps != num_steps:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):             # capture does not execute
+                if self.split is None:
+                    self.one_step(rt, num_steps)
+                else:
+                    self._prepare()
+                    self._fwd_out = self._forward(rt)
+            self.graph, self.graph_steps = g, num_steps
+        if self.split is None:
+            return self.graph.replay
+
+        def run():
+            self.graph.replay()
+            self._finish(self._fwd_out, num_steps)
+        return run
 
 
 def _expand(t: torch.Tensor, rows: int, T: int) -> torch.Tensor:
@@ -97,36 +146,39 @@ def fused_sample(sampler, den, x: torch.Tensor, cond: Dict, uc: Optional[Dict], 
     y = torch.cat((_expand(uc["vector"], N, T), _expand(cond["vector"], N, T)), 0)
     rt.set_conditioning(context, y)
 
-    if not USE_GRAPH or n < 3:
-        for _ in range(n):
-            st.one_step(rt, n)
-    else:
-        st.one_step(rt, n)                      # eager first step: allocates every buffer of the executor
-        if st.graph is None or st.graph_steps != n:
-            g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                st.one_step(rt, n)
-            st.graph, st.graph_steps = g, n     # capture does not execute
-        for _ in range(n - 1):
-            st.graph.replay()
+    _run_steps(st, rt, n)
     x.copy_(st.x)
     return x
 
 
+def _run_steps(st: _LoopState, rt, n: int):
+    if n < 3:
+        for _ in range(n):
+            st.one_step(rt, n)
+        return
+    st.one_step(rt, n)                          # eager first step: allocates every buffer of the executor
+    step = st.runner(rt, n)
+    for _ in range(n - 1):
+        step()
+
+
 def _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n: int, T: int) -> torch.Tensor:
-    """One clip, frames sharded over the ranks (vista_b200/sharded.py).  Every rank receives the same full-clip
-    inputs, advances its own frames and all-gathers the final latent."""
+    """One clip spread over the ranks (vista_b200/sharded.py): the frames are sharded, and with an even world size
+    the two CFG halves too.  Every rank receives the same full-clip inputs, advances the frames it owns and the
+    final latent is all-gathered."""
     from .sharded import gather_latent
     dev = x.device
     N, zc, h, w = x.shape
-    assert N == T, "frame-sharded sampling handles one clip"
+    assert N == T, "sharded sampling handles one clip"
     t0, t1 = rt.t0, rt.t1
     Tl = t1 - t0
+    half = getattr(rt, "cfg_half", None)
     states = rt.__dict__.setdefault("_loop_states", {})
     st = states.get((Tl, h, w))
     if st is None:
         st = states[(Tl, h, w)] = _LoopState(rt, Tl, h, w)
+        if half is not None:
+            st.configure_split(half, rt.pair_group)
     sigmas = sampler.discretization(n, device="cpu").to(torch.float32)
     x *= torch.sqrt(1.0 + sigmas[0] ** 2).to(dev)
     st.x.copy_(x[t0:t1])
@@ -142,10 +194,16 @@ def _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n: in
     st.concat_u.copy_(_expand(uc["concat"], N, T)[t0:t1])
     st.concat_c.copy_(_expand(cond["concat"], N, T)[t0:t1])
     st.scales.copy_(sampler.guider.scale_vector(T).to(dev, torch.float32)[t0:t1])
-    context = torch.cat((_expand(uc["crossattn"], N, T), _expand(cond["crossattn"], N, T)), 0)
-    y = torch.cat((_expand(uc["vector"], N, T), _expand(cond["vector"], N, T)), 0)
+    if half is None:
+        context = torch.cat((_expand(uc["crossattn"], N, T), _expand(cond["crossattn"], N, T)), 0)
+        y = torch.cat((_expand(uc["vector"], N, T), _expand(cond["vector"], N, T)), 0)
+    else:
+        src = uc if half == 0 else cond
+        context, y = _expand(src["crossattn"], N, T), _expand(src["vector"], N, T)
     rt.set_conditioning(context, y)
-    for _ in range(n):
-        st.one_step(rt, n)
-    x.copy_(gather_latent(st.x, T, group=rt.group))
+    _run_steps(st, rt, n)
+    if Tl == T:
+        x.copy_(st.x)
+    else:
+        x.copy_(gather_latent(st.x, T, group=rt.group))
     return x

@@ -98,6 +98,7 @@ SIGNATURES = {
     "b200v_attention_spatial_v3": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_groupnorm_chunk": [],
+    "b200v_groupnorm_chunk_for": [C.c_int32, C.c_int32],
     "b200v_groupnorm_sums": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P],
     "b200v_groupnorm_finalize": [_P, _I32, C.c_double, _F, _P, _P],
     "b200v_attention_temporal_sharded": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P],

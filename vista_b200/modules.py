@@ -88,12 +88,37 @@ class _RuntimeOwner:
         self._cond_cache = None
         self._shard_group = None
         self.frame_sharded = False
+        self._frame_world = 1
+        self.cfg_half = None          # 0: this rank runs the unconditional half of the CFG batch, 1: the conditional
+        self.pair_group = None        # the two ranks that own the same frames of the two halves
 
-    def enable_frame_sharding(self, group=None):
-        """Spread the frames of ONE clip over the ranks of `group` (BASELINE config 5); see vista_b200/sharded.py.
+    def enable_frame_sharding(self, group=None, cfg_split: Optional[bool] = None):
+        """Spread ONE clip over the ranks of `group` (BASELINE config 5); see vista_b200/sharded.py.
+        With an even world size the two halves of the classifier-free-guidance batch go to the two halves of
+        the ranks (no collective between them inside the UNet; the 4-channel network outputs of a frame's two
+        halves are exchanged once per step for the guidance), and the frames of each half are sharded over
+        world/2 ranks.  With an odd world size (or cfg_split=False) only the frames are sharded.
         Only the fused sampler drives this mode (every rank passes the same full-clip inputs)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if cfg_split is None:
+            cfg_split = world % 2 == 0
         self.frame_sharded = True
-        self._shard_group = group
+        self.cfg_half, self.pair_group = None, None
+        if cfg_split:
+            assert world % 2 == 0, "cfg_split needs an even number of ranks"
+            ranks = list(range(world)) if group is None else dist.get_process_group_ranks(group)
+            wf = world // 2
+            # every rank creates every group, in the same order
+            fgroups = [dist.new_group([ranks[hh * wf + i] for i in range(wf)]) for hh in range(2)]
+            pgroups = [dist.new_group([ranks[i], ranks[i + wf]]) for i in range(wf)]
+            self.cfg_half = rank // wf
+            self.pair_group = pgroups[rank % wf]
+            self._shard_group = fgroups[self.cfg_half]
+            self._frame_world = wf
+        else:
+            self._shard_group = group
+            self._frame_world = world
         self._rt_invalidate()
 
     def _rt_invalidate(self):
@@ -105,11 +130,13 @@ class _RuntimeOwner:
         key = (num_frames, str(device), id(model), self.frame_sharded)
         if self._runtime is None or self._runtime_key != key:
             cfg = _infer_config(model)
-            if self.frame_sharded:
+            if self.frame_sharded and self._frame_world > 1:
                 from .sharded import ShardedUNetRuntime
                 self._runtime = ShardedUNetRuntime(cfg, model.state_dict(), device, num_frames, group=self._shard_group)
             else:
                 self._runtime = UNetRuntime(cfg, model.state_dict(), device, num_frames)
+                self._runtime.t0, self._runtime.t1, self._runtime.group = 0, num_frames, None
+            self._runtime.cfg_half, self._runtime.pair_group = self.cfg_half, self.pair_group
             self._runtime_key = key
             self._cond_cache = None
         return self._runtime

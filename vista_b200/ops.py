@@ -198,6 +198,12 @@ def attention_temporal(q, k, v, out, nb: int, T: int, S: int, heads: int):
     return out
 
 
+def groupnorm_scratch(frames: int, tokens_per_frame: int, groups: int = 32) -> int:
+    """Doubles of partial-sum scratch b200v_groupnorm_stats needs for this shape."""
+    chunk = _lib.load().b200v_groupnorm_chunk_for(frames, tokens_per_frame)
+    return frames * (-(-tokens_per_frame // chunk)) * groups * 2
+
+
 class GNWorkspace:
     """Scratch for the two-phase GroupNorm: partial sums (grown on demand) and self-resetting ticket counters."""
 
@@ -224,8 +230,7 @@ def groupnorm(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float,
         ws = _default_ws.setdefault(x.device, GNWorkspace(x.device))
     if stats is None:
         stats = torch.empty(frames // frames_per_stat, groups, 2, dtype=torch.float32, device=x.device)
-    chunk = l.b200v_groupnorm_chunk()
-    ws.reserve(frames * (-(-tokens_per_frame // chunk)) * groups * 2)
+    ws.reserve(groupnorm_scratch(frames, tokens_per_frame, groups))
     assert frames // frames_per_stat <= ws.counters.numel()
     _count(2)
     _prof_begin("groupnorm", f"tokens={frames * tokens_per_frame} C={Cc} fps={frames_per_stat}", 0.0,
@@ -248,8 +253,7 @@ def groupnorm_sums(x, frames: int, tokens_per_frame: int, Cc: int, sums: torch.T
     l = _lib.load()
     if ws is None:
         ws = _default_ws.setdefault(x.device, GNWorkspace(x.device))
-    chunk = l.b200v_groupnorm_chunk()
-    ws.reserve(frames * (-(-tokens_per_frame // chunk)) * groups * 2)
+    ws.reserve(groupnorm_scratch(frames, tokens_per_frame, groups))
     _count(1)
     _lib.check(l.b200v_groupnorm_sums(x.data_ptr(), x.stride(0), frames, tokens_per_frame, Cc, groups, frames_per_stat,
                                       ws.partials.data_ptr(), ws.counters.data_ptr(), sums.data_ptr(), _stream()),

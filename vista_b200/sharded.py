@@ -15,6 +15,11 @@ The three temporal couplings of the UNet cross ranks:
 
 Weights are replicated.  The sampler state is frame-local too; the latent is all-gathered once at the end.
 torch.distributed (NCCL) is the transport; the math stays in the C-ABI kernels.
+
+With an even number of ranks the classifier-free-guidance batch is split first (modules.enable_frame_sharding):
+ranks [0, W/2) run the unconditional clip, ranks [W/2, W) the conditional one, each half sharding the frames
+over W/2 ranks with the collectives above inside its own sub-group; the only traffic between the halves is the
+4-channel network output of a rank's frames, exchanged pairwise once per step for the guidance (fused.py).
 """
 from __future__ import annotations
 
@@ -39,7 +44,10 @@ class ShardedUNetRuntime(UNetRuntime):
         self.t0, self.t1 = self.shards[self.rank]
         self.T_pad = max(b - a for a, b in self.shards)
         super().__init__(cfg, sd, device, num_frames=self.t1 - self.t0)     # self.T = local frames per clip
-        self.prev, self.next = halo_neighbours(self.rank, self.world)
+        prev, nxt = halo_neighbours(self.rank, self.world)
+        to_global = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
+        self.prev = None if prev is None else to_global(prev)       # P2POp peers are global ranks
+        self.next = None if nxt is None else to_global(nxt)
         self._tap_w: Dict[int, tuple] = {}
         self._frame_tables: Dict[tuple, torch.Tensor] = {}
         self.comm_bytes = 0

@@ -297,7 +297,7 @@ class UNetRuntime:
         if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] != B:
             self.gn_stats = torch.zeros(self.n_gn, B, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
             self.gn_ws = ops.GNWorkspace(self.dev)
-            self.gn_ws.reserve(B * (-(-h * w // 256)) * cfg.num_groups * 2)
+            self.gn_ws.reserve(ops.groupnorm_scratch(B, h * w, cfg.num_groups))
         # --- embeddings (video_model.py:456-471) + all emb_layers of the step in one GEMM
         temb = ops.timestep_embedding(c_noise, self.buf("emb.t", B, mc), mc)
         e_plain = self._mlp_step(temb, self.time_embed, "emb.plain")

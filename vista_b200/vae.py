@@ -153,7 +153,7 @@ class DecoderRuntime:
             self.gn_stats = torch.zeros(self.n_gn, T, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
             self.gn_ws = ops.GNWorkspace(self.dev)
         up_total = 2 ** (len(cfg.ch_mult) - 1)
-        self.gn_ws.reserve(T * (-(-h * w * up_total * up_total // 256)) * cfg.num_groups * 2)
+        self.gn_ws.reserve(ops.groupnorm_scratch(T, h * w * up_total * up_total, cfg.num_groups))
         M = T * h * w
         x = ops.conv3x3_small_cin(z_tokens, cfg.z_channels, self.conv_in_w, self.conv_in_b,
                                   self.buf("d.in", M, self.plan.block_in), T, h, w)
