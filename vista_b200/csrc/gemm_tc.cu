@@ -22,6 +22,7 @@ struct TGParams {
   int bw_sh, bh_sh;             // log2(BW), log2(BH): the box extents are powers of two (product 128)
   int tiles_w, tiles_h;
   int m_tiles, n_tiles;
+  int m_pairs;                  // ceil(m_tiles / 2): m-tile pairs of the 2-CTA schedule
   int ntaps, kc_per_tap;
   int dh[9], dw[9];
   int N, TN;
@@ -105,7 +106,7 @@ __device__ __forceinline__ int epi_group(int G, int wg, int k) {
 }
 
 // 10 warps are allocated as 12 (granularity 4): 65536 / 384 -> at most 168 registers per thread
-template <int ACT_, bool RV_, int NRES_, bool GEN>
+template <int ACT_, bool RV_, int NRES_, bool GEN, bool PAIR>
 __global__ void __launch_bounds__(320, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -119,8 +120,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* stages = smem + 1024;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
   const int KC = p.ntaps * p.kc_per_tap;
+  // Tile schedule.  1-CTA: CTA b walks tiles b, b + grid, ...; tile -> (m_blk, n_blk) = (tile / n_tiles, tile % n_tiles).
+  // CTA pair: cluster c walks pair-tiles; pair-tile -> m-tile pair (2 j, 2 j + 1) x n_blk, this CTA takes 2 j + rank
+  // (an odd m-tile count leaves one all-out-of-range tile: TMA zero fill, no rows stored).
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int total_tiles = (PAIR ? p.m_pairs : p.m_tiles) * p.n_tiles;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nstages; ++i) {
@@ -129,7 +136,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);
+      mbar_init(&tempty[i], PAIR ? 16 : 8);   // one arrival per epilogue warp (of both CTAs in a pair)
     }
     fence_barrier_init();
   }
@@ -137,7 +144,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (PAIR) {
+    cluster_sync_all();                       // both CTAs' barriers exist before anything can signal them
+    if (warp == 9) tmem_alloc_pair<512>(tmem_slot);
+  } else {
+    if (warp == 9) tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,25 +160,37 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = kABytes + p.TN * 128;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      const int b_rows = PAIR ? (p.TN >> 1) : p.TN;           // B rows this CTA stages
+      const uint32_t tx = PAIR ? 2u * (kABytes + b_rows * 128) : (uint32_t)(kABytes + b_rows * 128);
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int mq = tile / p.n_tiles, n_blk = tile - mq * p.n_tiles;
+        const int m_blk = PAIR ? 2 * mq + (int)cta_rank : mq;
         const int tw = m_blk % p.tiles_w;
         const int th = (m_blk / p.tiles_w) % p.tiles_h;
         const int tb = m_blk / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.BW, h0 = th * p.BH, b0 = tb * p.BB;
+        const int n0 = n_blk * p.TN + (PAIR ? (int)cta_rank * b_rows : 0);
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
           uint8_t* sA = stages + stage * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
-          mbar_expect_tx(&full[stage], tx);
           const int tap = kc / p.kc_per_tap;
           const int c0 = (kc - tap * p.kc_per_tap) * 64;
-          if (p.a_mode == 0)
-            tma_load_2d(sA, &tmA, &full[stage], c0, w0);
-          else
-            tma_load_4d(sA, &tmA, &full[stage], c0, w0 + p.dw[tap], h0 + p.dh[tap], b0);
-          tma_load_2d(sB, &tmB, &full[stage], kc * 64, n_blk * p.TN);
+          if (PAIR) {
+            if (cta_rank == 0) mbar_expect_tx(&full[stage], tx);   // bytes of both CTAs land on the leader's barrier
+            if (p.a_mode == 0)
+              tma_load_2d_pair(sA, &tmA, &full[stage], c0, w0);
+            else
+              tma_load_4d_pair(sA, &tmA, &full[stage], c0, w0 + p.dw[tap], h0 + p.dh[tap], b0);
+            tma_load_2d_pair(sB, &tmB, &full[stage], kc * 64, n0);
+          } else {
+            mbar_expect_tx(&full[stage], tx);
+            if (p.a_mode == 0)
+              tma_load_2d(sA, &tmA, &full[stage], c0, w0);
+            else
+              tma_load_4d(sA, &tmA, &full[stage], c0, w0 + p.dw[tap], h0 + p.dh[tap], b0);
+            tma_load_2d(sB, &tmB, &full[stage], kc * 64, n0);
+          }
           if (++stage == p.nstages) {
             stage = 0;
             phase ^= 1;
@@ -175,14 +199,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (CTA pair: the leader only)
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      const uint32_t idesc = make_idesc_f16(128, p.TN, p.bf16, 0, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, p.TN, p.bf16, 0, 0);
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         mbar_wait(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
@@ -195,15 +219,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) {
             const uint64_t ad = make_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t bd = make_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_f16(d_tmem, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
+            if (PAIR)
+              umma_f16_pair(d_tmem, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
+            else
+              umma_f16(d_tmem, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == p.nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (PAIR) umma_commit_pair(&tfull[as]); else umma_commit(&tfull[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -238,8 +267,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const char* r1p = reinterpret_cast<const char*>(p.res1);
     const char* r2p = reinterpret_cast<const char*>(p.res2);
     const bool has_bias = p.bias != nullptr;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const int mq = tile / p.n_tiles, n_blk = tile - mq * p.n_tiles;
+      const int m_blk = PAIR ? 2 * mq + (int)cta_rank : mq;
       int token_own, valid_own;
       if (p.a_mode == 0) {
         token_own = m_blk * 128 + r;
@@ -394,16 +424,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
       tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      __syncwarp();
+      if (lane == 0) {                            // the accumulator stage of this CTA is drained
+        if (PAIR) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -465,10 +499,15 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     uint32_t es[4] = {1, 1, 1, 1};
     if (encode_tmap_16bit(&tmA, d->a, 4, dims, strides, box, es, d->bf16)) return 3;
   }
+  // CTA pairs (cta_group::2, M = 256 per MMA) halve the shared-memory operand traffic per SM; used whenever there
+  // are at least two m-tiles.  VB_GEMM_PAIR=0 forces the 1-CTA kernel (A/B comparison, debugging).
+  static const bool pair_enabled = !(getenv("VB_GEMM_PAIR") && atoi(getenv("VB_GEMM_PAIR")) == 0);
+  const bool pair = pair_enabled && p.m_tiles >= 2;
+  const int b_rows = pair ? d->tile_n / 2 : d->tile_n;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {64, (uint32_t)d->tile_n};
+    uint32_t box[2] = {64, (uint32_t)b_rows};
     uint32_t es[2] = {1, 1};
     if (encode_tmap_16bit(&tmB, d->b, 2, dims, strides, box, es, d->bf16)) return 3;
   }
@@ -482,7 +521,8 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   p.TN = d->tile_n;
   p.n_tiles = (d->N + d->tile_n - 1) / d->tile_n;
   p.bf16 = d->bf16;
-  p.stage_bytes = kABytes + ((d->tile_n * 128 + 1023) / 1024) * 1024;
+  p.m_pairs = (p.m_tiles + 1) / 2;
+  p.stage_bytes = kABytes + ((b_rows * 128 + 1023) / 1024) * 1024;
   constexpr int kStagingBytes = 8 * 32 * 128;  // epilogue transpose buffers (8 warps x 32 rows x 32 fp32)
   p.nstages = (227 * 1024 - 2048 - kStagingBytes) / p.stage_bytes;
   if (p.nstages > kMaxStages) p.nstages = kMaxStages;
@@ -505,10 +545,13 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   // Epilogue variant: the common fp16 feature sets are compiled in (no per-element feature tests), everything
   // else (bf16 operands, fp32 output, unusual combinations) takes the generic instantiation.
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const TGParams);
-  static const Kern kVariants[8] = {
-      tapgemm_kernel<0, false, 0, false>, tapgemm_kernel<0, false, 1, false>, tapgemm_kernel<0, false, 2, false>,
-      tapgemm_kernel<0, true, 0, false>,  tapgemm_kernel<0, true, 1, false>,  tapgemm_kernel<1, false, 0, false>,
-      tapgemm_kernel<2, false, 0, false>, tapgemm_kernel<0, true, 2, true>};
+#define VB_VARIANTS(PAIR)                                                                                         \
+  {tapgemm_kernel<0, false, 0, false, PAIR>, tapgemm_kernel<0, false, 1, false, PAIR>,                            \
+   tapgemm_kernel<0, false, 2, false, PAIR>, tapgemm_kernel<0, true, 0, false, PAIR>,                             \
+   tapgemm_kernel<0, true, 1, false, PAIR>,  tapgemm_kernel<1, false, 0, false, PAIR>,                            \
+   tapgemm_kernel<2, false, 0, false, PAIR>, tapgemm_kernel<0, true, 2, true, PAIR>}
+  static const Kern kVariants[2][8] = {VB_VARIANTS(false), VB_VARIANTS(true)};
+#undef VB_VARIANTS
   int variant = 7;
   if (!d->bf16 && !d->out_f32 && !getenv("VB_GEMM_GENERIC")) {
     const int nres = (d->res1 ? 1 : 0) + (d->res2 ? 1 : 0);
@@ -518,15 +561,41 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     else if (d->act == 2) variant = 6;
   }
   static bool attr_set = false;
+  static int max_clusters = 0;
   if (!attr_set) {
-    for (int i = 0; i < 8; ++i)
-      VB_CHECK_CUDA(cudaFuncSetAttribute(kVariants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int q = 0; q < 2; ++q)
+      for (int i = 0; i < 8; ++i)
+        VB_CHECK_CUDA(cudaFuncSetAttribute(kVariants[q][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // how many CTA pairs the device runs at once (pairs sit on the two SMs of a TPC)
+    cudaLaunchConfig_t qc = {};
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.gridDim = dim3(2 * device_sm_count()); qc.blockDim = dim3(320); qc.dynamicSmemBytes = 227 * 1024;
+    qc.attrs = qa; qc.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kVariants[1][0], &qc) != cudaSuccess || max_clusters <= 0) {
+      cudaGetLastError();
+      max_clusters = device_sm_count() / 2;
+    }
     attr_set = true;
   }
-  const long long total = (long long)p.m_tiles * p.n_tiles;
-  int grid = device_sm_count();
-  if (total < grid) grid = (int)total;
-  kVariants[variant]<<<grid, 320, smem_bytes, stream>>>(tmA, tmB, p);
+  if (pair) {
+    const long long total = (long long)p.m_pairs * p.n_tiles;
+    int clusters = max_clusters;
+    if (total < clusters) clusters = (int)total;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kVariants[1][variant], tmA, tmB, p));
+  } else {
+    const long long total = (long long)p.m_tiles * p.n_tiles;
+    int grid = device_sm_count();
+    if (total < grid) grid = (int)total;
+    kVariants[0][variant]<<<grid, 320, smem_bytes, stream>>>(tmA, tmB, p);
+  }
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
