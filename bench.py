@@ -228,7 +228,7 @@ def run_ours(args):
     decode_s = None
     try:
         from vista_b200.vae import bench_decode
-        decode_s = bench_decode(dcfg, rand_sd, dev, T, h, w)
+        decode_s = bench_decode(dcfg, rand_sd, dev, T, h, w, parallel=world > 1)   # N > 1: chunks dealt out over the ranks
     except ImportError:
         pass
 
@@ -250,9 +250,10 @@ def run_ours(args):
     d2h = res.numel() * res.element_size()
 
     if world > 1:
-        tmax = torch.tensor([dt, e2e_dt], device=dev)
+        tmax = torch.tensor([dt, e2e_dt, decode_s or 0.0], device=dev)
         torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
         dt, e2e_dt = float(tmax[0]), float(tmax[1])
+        decode_s = float(tmax[2]) if decode_s is not None else None
     step_s = dt / K
     e2e_step_s = e2e_dt / K
 
@@ -266,10 +267,10 @@ def run_ours(args):
         shard_desc = (f"one clip over {world} GPUs: CFG halves x frames ({world // 2} frame shard(s) per half); per step a "
                       f"pairwise all-gather of the 4-channel network output" +
                       ("" if world == 2 else ", and inside each half temporal K/V all-gather, GN-sum all-reduce, 1-frame halos") +
-                      " (NCCL); decode on rank 0")
+                      " (NCCL); decode chunks dealt out over the ranks")
     else:
         shard_desc = (f"frames of one clip over {world} GPUs: temporal K/V all-gather, GN-sum all-reduce, 1-frame halos "
-                      f"(NCCL); decode on rank 0")
+                      f"(NCCL); decode chunks dealt out over the ranks")
     peaks = load_peaks()
     full = args.config == "full"
     ach = (F_STEP_TFLOP / step_s) if full else None

@@ -188,8 +188,9 @@ int b200v_blend_emb(const float* e_plain, const float* e_cond, const float* labe
  * ---------------------------------------------------------------------------------------------- */
 int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask,
                           const float* concat_u /* uncond rows (T,4,h,w) or NULL = zeros */,
-                          const float* concat_c /* cond rows (T,4,h,w) or NULL = zeros */, const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
-                          int32_t T, int32_t h, int32_t w, void* stream);
+                          const float* concat_c /* cond rows (T,4,h,w) or NULL = zeros */, const float* sigmas, const int32_t* step_idx,
+                          void* unet_in_f16 /* [2T*h*w] rows of 8 fp16, row stride ld_in elements */, int64_t ld_in,
+                          float* c_noise, int32_t T, int32_t h, int32_t w, void* stream);
 int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, ld_net] fp32 token-major, 4 channels used */,
                          int64_t ld_net, const float* cond_frame, const float* mask, const float* scales /* [T] */, const float* sigmas, int32_t* step_idx,
                          int32_t num_steps, int32_t T, int32_t h, int32_t w, void* stream);

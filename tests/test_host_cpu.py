@@ -87,7 +87,10 @@ def test_tile_pickers():
         assert bw * bh * bb == 128
     assert ops.pick_box(128, 72, 50)[1] * ops.pick_box(128, 72, 50)[0] == 128
     assert ops.pick_box(32, 18, 50) == (32, 2, 2)      # exact cover: 225 tiles
-    assert ops.pick_tile_n(320) == 160 and ops.pick_tile_n(960) in (192, 240, 160) and ops.pick_tile_n(2560, True) == 256
+    # tile widths follow the measured cost of one MMA, t(n) = 61 + 0.22 max(n, 128) ns: wide tiles win even with a
+    # partly empty last tile (profiles/r01_umma_n_sweep.md)
+    assert ops.pick_tile_n(320) == 160 and ops.pick_tile_n(640) == 224 and ops.pick_tile_n(960) == 256
+    assert ops.pick_tile_n(1920) == 256 and ops.pick_tile_n(1280) == 256 and ops.pick_tile_n(2560, True) == 256
     for n in (64, 96, 320, 640, 1280, 3840, 2560, 5120, 10240):
         tn = ops.pick_tile_n(n)
         assert 32 <= tn <= 256 and tn % 32 == 0

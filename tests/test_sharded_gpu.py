@@ -50,6 +50,17 @@ def _worker(rank, world, port, q):
                       cond_frame=torch.from_numpy(z).to(dev), cond_mask=torch.from_numpy(mask).to(dev))
             torch.cuda.synchronize()
             res[mode] = out.cpu()
+        # chunk-parallel decode (rank r decodes chunks r, r + W, ...) must equal the serial chunked decode bit for bit
+        from helpers import decoder_weights
+        from vista_b200.vae import DecoderRuntime, decode_first_stage, decode_first_stage_parallel
+        dcfg, dsd = decoder_weights("tiny")
+        drt = DecoderRuntime(dcfg, to_t(dsd), dev)
+        zz = torch.from_numpy(synth.normal(9, "decfs.z", (25, dcfg.z_channels, 8, 16), std=0.18215)).to(dev)
+        serial = decode_first_stage(drt, zz).cpu()
+        par = decode_first_stage_parallel(drt, zz).cpu()
+        torch.cuda.synchronize()
+        assert torch.equal(serial, par), "parallel decode differs from the serial decode"
+        assert rel_l2(par, torch.from_numpy(golden("decode_first_stage_tiny")["out"])) < 5e-3
         q.put((rank, res["single"].numpy(), res["frames"].numpy(), res["split"].numpy()))
     finally:
         dist.destroy_process_group()

@@ -31,6 +31,14 @@ if "conv" in which:
     out = torch.empty(M, C, dtype=torch.float16, device=dev)
     for _ in range(2):
         ops.gemm(x, w, out, bias=b, taps=ops.TAPS_3X3, geom=(128, 72, 50))
+if "conv1280" in which:
+    M2, C2 = 28800, 1280
+    x2 = (torch.randn(M2, C2, device=dev) * 0.5).half()
+    w = (torch.randn(C2, 9 * C2, device=dev) * (9 * C2) ** -0.5).half()
+    b = torch.randn(C2, device=dev) * 0.05
+    out = torch.empty(M2, C2, dtype=torch.float16, device=dev)
+    for _ in range(2):
+        ops.gemm(x2, w, out, bias=b, taps=ops.TAPS_3X3, geom=(32, 18, 50))
 if "attn" in which:
     qkv = torch.randn(M, 3 * C, device=dev).half()
     o = torch.empty(M, C, dtype=torch.float16, device=dev)

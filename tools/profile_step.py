@@ -19,7 +19,9 @@ rt = UNetRuntime(ucfg, rand_sd(spec.unet_param_specs(ucfg)), dev, T)
 ctx = torch.randn(B, 1, 3456, device=dev)
 y = torch.randn(B, ucfg.adm_in_channels, device=dev)
 rt.set_conditioning(ctx, y)
-tok = torch.randn(B * h * w, 8, device=dev).half()
+from vista_b200.unet import padded_input_rows
+tok = padded_input_rows(B * h * w, dev)          # the production layout (fused sampler): input conv on the tensor cores
+tok.copy_(torch.randn(B * h * w, 8, device=dev).half())
 cn = torch.full((B,), 0.5, device=dev)
 mask = torch.zeros(B, device=dev); mask[0] = mask[T] = 1
 for _ in range(2):

@@ -206,6 +206,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int as = 0;
       uint32_t aphase = 0;
       const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, p.TN, p.bf16, 0, 0);
+      // Shared-memory descriptors (make_desc_sw128(addr, 16, 1024)): the high word is constant, the low word is
+      // (addr >> 4) | LBO; it advances by stage_bytes >> 4 per pipeline stage and by 2 (32 bytes) per K = 16 step.
+      // Kept incrementally so that the single issuing thread spends a handful of instructions per MMA.
+      const uint64_t desc_hi = make_desc_sw128(0, 16, 1024) & 0xFFFFFFFF00000000ull;
+      const uint32_t a_lo0 = (uint32_t)(make_desc_sw128(smem_u32(stages), 16, 1024) & 0xFFFFFFFFull);
+      const uint32_t lo_step = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t b_off = kABytes >> 4;
+      uint32_t a_lo = a_lo0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         mbar_wait(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
@@ -213,12 +221,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(stages + stage * p.stage_bytes);
-          const uint32_t b_base = a_base + kABytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t bd = make_desc_sw128(b_base + k * 32, 16, 1024);
+            const uint64_t ad = desc_hi | (uint64_t)(a_lo + 2 * k);
+            const uint64_t bd = desc_hi | (uint64_t)(a_lo + b_off + 2 * k);
             if (PAIR)
               umma_f16_pair(d_tmem, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
             else
@@ -226,9 +232,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+          a_lo += lo_step;
           if (++stage == p.nstages) {
             stage = 0;
             phase ^= 1;
+            a_lo = a_lo0;
           }
         }
         // accumulator complete -> epilogue (of both CTAs)
@@ -320,6 +328,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (gidx < 0) break;
         const int c0 = gidx * 32;
         if (k + 1 < 4) prefetch_res(k + 1, rpre[(k + 1) & 1]);
+        if (n_out_base + c0 >= n_out_total) continue;   // group entirely beyond N (last n-tile of a padded N)
         // ---------------- phase A
         if (act != 2) {
           uint32_t v[32];
@@ -499,9 +508,10 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     uint32_t es[4] = {1, 1, 1, 1};
     if (encode_tmap_16bit(&tmA, d->a, 4, dims, strides, box, es, d->bf16)) return 3;
   }
-  // CTA pairs (cta_group::2, M = 256 per MMA) halve the shared-memory operand traffic per SM; used whenever there
-  // are at least two m-tiles.  VB_GEMM_PAIR=0 forces the 1-CTA kernel (A/B comparison, debugging).
-  static const bool pair_enabled = !(getenv("VB_GEMM_PAIR") && atoi(getenv("VB_GEMM_PAIR")) == 0);
+  // CTA pairs (cta_group::2, M = 256 per MMA) halve the shared-memory operand traffic per SM.  Measured on B200
+  // (profiles/r01_gemm_pair_vs_single.md) the pair kernel is on par for the large-K convolutions and slower for
+  // the small-K projections (the two epilogues of a pair gate each other), so it is opt-in: VB_GEMM_PAIR=1.
+  static const bool pair_enabled = getenv("VB_GEMM_PAIR") && atoi(getenv("VB_GEMM_PAIR")) != 0;
   const bool pair = pair_enabled && p.m_tiles >= 2;
   const int b_rows = pair ? d->tile_n / 2 : d->tile_n;
   {

@@ -641,7 +641,8 @@ __global__ void blend_emb_kernel(const float* __restrict__ e_plain, const float*
 __global__ void sampler_prepare_kernel(float* __restrict__ x, const float* __restrict__ cond_frame,
                                        const float* __restrict__ mask, const float* __restrict__ concat_u,
                                        const float* __restrict__ concat_c, const float* __restrict__ sigmas, const int* __restrict__ step_idx,
-                                       __half* __restrict__ unet_in, float* __restrict__ c_noise, int T, int h, int w) {
+                                       __half* __restrict__ unet_in, long long ld_in, float* __restrict__ c_noise, int T,
+                                       int h, int w) {
   const float sigma = sigmas[*step_idx];
   const float c_in = rsqrtf(sigma * sigma + 1.0f);
   const int hw = h * w;
@@ -665,8 +666,8 @@ __global__ void sampler_prepare_kernel(float* __restrict__ x, const float* __res
     xv[4 + c] = concat_u ? concat_u[idx] : 0.f;        // uncond rows (zeros in sample.py:243)
     cu[4 + c] = concat_c ? concat_c[idx] : 0.f;        // cond rows
   }
-  *reinterpret_cast<uint4*>(unet_in + ((long long)t * hw + pix) * 8) = f_to_h8(xv);
-  *reinterpret_cast<uint4*>(unet_in + (((long long)T + t) * hw + pix) * 8) = f_to_h8(cu);
+  *reinterpret_cast<uint4*>(unet_in + ((long long)t * hw + pix) * ld_in) = f_to_h8(xv);
+  *reinterpret_cast<uint4*>(unet_in + (((long long)T + t) * hw + pix) * ld_in) = f_to_h8(cu);
 }
 
 __global__ void sampler_update_kernel(float* __restrict__ x, const float* __restrict__ net,
@@ -969,12 +970,13 @@ extern "C" int b200v_blend_emb(const float* e_plain, const float* e_cond, const 
 }
 
 extern "C" int b200v_sampler_prepare(float* x, const float* cond_frame, const float* mask, const float* concat_u,
-                                     const float* concat_c, const float* sigmas, const int32_t* step_idx, void* unet_in_f16, float* c_noise,
-                                     int32_t T, int32_t h, int32_t w, void* stream) {
+                                     const float* concat_c, const float* sigmas, const int32_t* step_idx, void* unet_in_f16,
+                                     int64_t ld_in, float* c_noise, int32_t T, int32_t h, int32_t w, void* stream) {
   VB_REQUIRE(x && sigmas && step_idx && unet_in_f16, "sampler_prepare: null pointer");
+  VB_REQUIRE(ld_in >= 8 && ld_in % 8 == 0, "sampler_prepare: ld_in must be a multiple of 8");
   const long long total = (long long)T * h * w;
   sampler_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, cond_frame, mask, concat_u, concat_c, sigmas, step_idx, (__half*)unet_in_f16, c_noise, T, h, w);
+      x, cond_frame, mask, concat_u, concat_c, sigmas, step_idx, (__half*)unet_in_f16, ld_in, c_noise, T, h, w);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

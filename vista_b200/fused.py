@@ -17,6 +17,7 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
+from .unet import padded_input_rows
 
 USE_GRAPH = os.environ.get("VISTA_B200_GRAPH", "1") != "0"
 
@@ -38,7 +39,7 @@ class _LoopState:
         self.sigmas = torch.zeros(1024, **f32)
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.c_noise = torch.empty(2 * N, **f32)
-        self.unet_in = torch.empty(2 * N * h * w, 8, dtype=torch.float16, device=dev)
+        self.unet_in = padded_input_rows(2 * N * h * w, dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_steps = None
         # CFG-split mode (modules.enable_frame_sharding): this rank runs one half of the doubled batch

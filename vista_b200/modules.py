@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import ops
 from .spec import UNetConfig, unet_param_specs
-from .unet import UNetRuntime
+from .unet import UNetRuntime, padded_input_rows
 
 
 class _Node(nn.Module):
@@ -157,7 +157,10 @@ class _RuntimeOwner:
                 or not (torch.equal(cc[0], context) and torch.equal(cc[1], y)):
             rt.set_conditioning(context, y)
             self._cond_cache = (context.detach().clone(), y.detach().clone())
-        tok = rt.buf("io.x", B * h * w, 8)
+        key = ("io.x", B * h * w)
+        tok = rt._bufs.get(key)
+        if tok is None:
+            tok = rt._bufs[key] = padded_input_rows(B * h * w, x.device)
         if Cin < 8:
             tok.zero_()
         ops.nchw_to_tokens(x.float().contiguous(), tok, B, Cin, h, w)

@@ -105,14 +105,16 @@ def pick_box(W: int, H: int, NB: int) -> Tuple[int, int, int]:
 
 
 def pick_tile_n(N: int, geglu: bool = False) -> int:
-    """Largest tile_n <= 256 (multiple of 32, of 64 for GEGLU) that wastes the least of N."""
+    """tile_n <= 256 (multiple of 32, of 64 for GEGLU) minimising the MMA time of one row of n-tiles under the
+    measured cost of a 128 x tile_n x 16 tcgen05.mma, t(n) = 61 + 0.22 * max(n, 128) ns
+    (profiles/r01_umma_n_sweep.md): wide tiles win even when the last one is partly empty."""
     step = 64 if geglu else 32
     best, best_cost = None, None
     for tn in range(256, step - 1, -step):
         if geglu and N % tn:
             continue
         tiles = -(-N // tn)
-        cost = (tiles * tn - N, tiles)
+        cost = (round(tiles * (61.0 + 0.22 * max(tn, 128)), 3), tiles, tiles * tn - N)
         if best_cost is None or cost < best_cost:
             best, best_cost = tn, cost
     if best is None:
@@ -358,7 +360,7 @@ def sampler_prepare(x, cond_frame, mask, concat_u, concat_c, sigmas, step_idx, u
     _prof_begin("other", "sampler_prepare", 0.0, 0.0)
     _lib.check(_lib.load().b200v_sampler_prepare(x.data_ptr(), _ptr(cond_frame), _ptr(mask), _ptr(concat_u),
                                                  _ptr(concat_c), sigmas.data_ptr(), step_idx.data_ptr(), unet_in.data_ptr(),
-                                                 _ptr(c_noise), T, h, w, _stream()), "b200v_sampler_prepare")
+                                                 unet_in.stride(0), _ptr(c_noise), T, h, w, _stream()), "b200v_sampler_prepare")
     _prof_end()
 
 

@@ -37,6 +37,15 @@ class Lin:
     geglu: bool = False
 
 
+IN_PAD = 64   # token rows of the network input: 8 channels used, zero padded to one 64-channel K chunk
+
+
+def padded_input_rows(rows: int, device) -> torch.Tensor:
+    """[rows, 8] fp16 view (row stride IN_PAD) of a zeroed buffer: what UNetRuntime.forward wants as x_tokens so
+    that the input convolution is a tap-GEMM; the pad columns must stay zero."""
+    return torch.zeros(rows, IN_PAD, dtype=torch.float16, device=device)[:, :8]
+
+
 class UNetRuntime:
     """Device-resident, repacked VideoUNet.  One instance per (weights, num_frames)."""
 
@@ -120,8 +129,15 @@ class UNetRuntime:
                 self.layers[p] = L
             elif isinstance(layer, ConvSpec):
                 if layer.kind == "conv_in":
-                    self.layers[layer.prefix] = dict(spec=layer, w=self._f32(f"{layer.prefix}.weight"),
-                                                     b=self._f32(f"{layer.prefix}.bias"))
+                    # two forms: fp32 [Cout, Cin, 3, 3] for the thin direct kernel (8-wide token rows), and a tap-GEMM
+                    # weight with Cin zero-padded to 64 for callers that hand in IN_PAD-wide, zero-padded rows
+                    w = self._f32(f"{layer.prefix}.weight")
+                    wp = torch.zeros(w.shape[0], IN_PAD, 3, 3, dtype=torch.float32, device=self.dev)
+                    wp[:, :w.shape[1]] = w
+                    b = self._f32(f"{layer.prefix}.bias")
+                    self.layers[layer.prefix] = dict(spec=layer, w=w, b=b,
+                                                     conv=Lin(conv_weight_to_taps(wp).to(torch.float16).contiguous(), b,
+                                                              ops.pick_tile_n(w.shape[0])))
                 else:
                     self.layers[layer.prefix] = dict(spec=layer, conv=self._lin(layer.prefix))
         self.emb_all = Lin(torch.cat(emb_w, 0).to(torch.float16).contiguous(), torch.cat(emb_b, 0).contiguous(),
@@ -287,8 +303,9 @@ class UNetRuntime:
     # ------------------------------------------------------------------ forward
     def forward(self, x_tokens: torch.Tensor, c_noise: torch.Tensor, cond_mask: Optional[torch.Tensor],
                 h: int, w: int, net_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x_tokens: [(B h w), 8] fp16 (x*c_in | concat); c_noise: [B] fp32; returns [(B h w), 8] fp32 whose
-        first out_channels columns are the network output."""
+        """x_tokens: [(B h w), 8] fp16 (x*c_in | concat), either contiguous or a view of zero-padded IN_PAD-wide rows
+        (padded_input_rows); c_noise: [B] fp32; returns [(B h w), 8] fp32 whose first out_channels columns are the
+        network output."""
         assert self.cond is not None, "call set_conditioning() first"
         cfg, T = self.cfg, self.T
         B = c_noise.numel()
@@ -347,7 +364,11 @@ class UNetRuntime:
                 elif layer.kind == "up":
                     x = self._up(L, x, dst, B, bh, bw)
                 elif layer.kind == "conv_in":
-                    x = ops.conv3x3_small_cin(x, layer.cin, L["w"], L["b"], dst, B, bh, bw)
+                    if x.stride(0) == IN_PAD:      # zero-padded rows: the input conv runs on the tensor cores
+                        a = x.as_strided((x.shape[0], IN_PAD), (IN_PAD, 1))
+                        x = self.gemm(a, L["conv"], dst, taps=ops.TAPS_3X3, geom=(bw, bh, B))
+                    else:
+                        x = ops.conv3x3_small_cin(x, layer.cin, L["w"], L["b"], dst, B, bh, bw)
             return x
 
         # --- input blocks: block i writes into the skip slice of output block (n-1-i)

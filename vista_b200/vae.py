@@ -195,21 +195,67 @@ def decode_first_stage(rt: DecoderRuntime, z: torch.Tensor, scale_factor: float 
             blend[:n_overlap] = 1
         rt.forward(tok, T, h, w, out, out_frame0=out_frame0, blend=blend)
 
+    for f0, n, o0, nov in _decode_chunks(F_, n_samples, overlap):
+        run(zs[f0:f0 + n], o0, nov)
+    return out
+
+
+def _decode_chunks(F_: int, n_samples: int, overlap: int):
+    """Chunk plan of decode_first_stage (vwm/models/diffusion.py:150-180): (first input frame, frame count,
+    first output frame, overlapping frames that are averaged with the previous chunk's output)."""
+    chunks = []
     if overlap < n_samples:
-        prev = zs[:overlap]
-        pos = overlap
-        first = True
-        for cur in zs[overlap:].split(n_samples - overlap, dim=0):
-            ctx = torch.cat((prev, cur), dim=0)
-            prev = cur[-overlap:]
-            run(ctx, pos - overlap, 0 if first else overlap)
-            pos += cur.shape[0]
+        pos, first, prev_len = overlap, True, overlap
+        while pos < F_:
+            cur = min(n_samples - overlap, F_ - pos)
+            # context = the last prev_len frames before pos (prev = cur[-overlap:] of the previous chunk) + cur
+            chunks.append((pos - prev_len, prev_len + cur, pos - overlap, 0 if first else overlap))
+            pos += cur
+            prev_len = min(overlap, cur)
             first = False
     else:
         pos = 0
-        for cur in zs.split(n_samples, dim=0):
-            run(cur, pos, 0)
-            pos += cur.shape[0]
+        while pos < F_:
+            cur = min(n_samples, F_ - pos)
+            chunks.append((pos, cur, pos, 0))
+            pos += cur
+    return chunks
+
+
+def decode_first_stage_parallel(rt: DecoderRuntime, z: torch.Tensor, scale_factor: float = 0.18215,
+                                n_samples: Optional[int] = 14, overlap: int = 3, group=None) -> torch.Tensor:
+    """decode_first_stage with the chunks dealt out over the ranks of `group`: the chunks are independent up to the
+    overlap rule (out = (previous + new) / 2 on the first `overlap` frames of a chunk), so rank r decodes chunks
+    r, r + W, ... unblended, the owners broadcast them, and every rank assembles the clip in chunk order with the
+    same arithmetic as the serial path (bit-identical result on every rank).  Every rank passes the same z."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    F_, zc, h, w = z.shape
+    n_samples = F_ if n_samples is None else n_samples
+    up = 2 ** (len(rt.cfg.ch_mult) - 1)
+    out = torch.empty(F_, rt.cfg.out_ch, h * up, w * up, dtype=torch.float32, device=z.device)
+    zs = (z.float() / scale_factor).contiguous()
+    chunks = _decode_chunks(F_, n_samples, overlap)
+    if any(nov > n or o0 != f0 for f0, n, o0, nov in chunks):
+        raise NotImplementedError("decode_first_stage_parallel: chunks shorter than the overlap")
+    to_global = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
+    bufs = []
+    for i, (f0, n, o0, nov) in enumerate(chunks):
+        cb = rt.__dict__.setdefault("_chunk_out", {}).get((i, n))
+        if cb is None:
+            cb = rt._chunk_out[(i, n)] = torch.empty(n, rt.cfg.out_ch, h * up, w * up, dtype=torch.float32, device=z.device)
+        bufs.append(cb)
+        if i % world == rank:
+            tok = rt.buf("d.z", n * h * w, 8)
+            tok.zero_()
+            ops.nchw_to_tokens(zs[f0:f0 + n].contiguous(), tok, n, zc, h, w)
+            rt.forward(tok, n, h, w, cb)
+    for i, (f0, n, o0, nov) in enumerate(chunks):
+        if world > 1:
+            dist.broadcast(bufs[i], src=to_global(i % world), group=group)
+        if nov:
+            out[o0:o0 + nov] = 0.5 * (out[o0:o0 + nov] + bufs[i][:nov])
+        out[o0 + nov:o0 + n] = bufs[i][nov:]
     return out
 
 
@@ -262,17 +308,22 @@ class VideoDecoder(nn.Module):
         return self.conv_out.time_mix_conv.weight if not skip_time_mix else self.conv_out.weight
 
 
-def bench_decode(dcfg: DecoderConfig, rand_sd, dev, T: int, h: int, w: int, reps: int = 1) -> float:
-    """Seconds for one chunked decode of a T-frame clip (warm)."""
+def bench_decode(dcfg: DecoderConfig, rand_sd, dev, T: int, h: int, w: int, reps: int = 1, parallel: bool = False) -> float:
+    """Seconds for one chunked decode of a T-frame clip (warm).  parallel: chunks dealt out over the ranks of the
+    default process group (every rank must call; the caller takes the max over ranks)."""
     sd = rand_sd(decoder_param_specs(dcfg))
     rt = DecoderRuntime(dcfg, sd, dev)
     z = torch.randn(T, dcfg.z_channels, h, w, device=dev) * 0.18215
-    decode_first_stage(rt, z)
+    if parallel:
+        import torch.distributed as dist
+        dist.broadcast(z, src=0)
+    fn = (lambda: decode_first_stage_parallel(rt, z)) if parallel else (lambda: decode_first_stage(rt, z))
+    fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        decode_first_stage(rt, z)
+        fn()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 1e3 / reps
