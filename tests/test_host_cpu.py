@@ -177,7 +177,8 @@ def test_kernel_register_budgets_fit_their_launch_shape():
     from vista_b200 import lib
     lib.build()
     out = subprocess.run(["cuobjdump", "--dump-resource-usage", lib.LIB_PATH], capture_output=True, text=True).stdout
-    blocks = {"tapgemm_kernel": 320, "attn2_spatial_kernel": 320, "attn3_spatial_kernel": 768, "attn_spatial_kernel": 192, "attn_temporal_kernel": 128,
+    blocks = {"tapgemm_kernel": 320,   # instantiations with 16 epilogue warps (last template argument 4) launch 576
+              "attn2_spatial_kernel": 320, "attn3_spatial_kernel": 768, "attn_spatial_kernel": 192, "attn_temporal_kernel": 128,
               "gn_stats_kernel": 256, "gn_apply_kernel": 256, "layernorm_kernel": 256}
     found = 0
     lines = out.splitlines()
@@ -187,6 +188,8 @@ def test_kernel_register_budgets_fit_their_launch_shape():
                 m = re.search(r"REG:(\d+)", lines[i + 1])
                 assert m, lines[i + 1]
                 regs = int(m.group(1))
+                if name == "tapgemm_kernel" and re.search(r"Li4EEEv", line):
+                    threads = 576
                 per_warp = -(-regs * 32 // 256) * 256            # register allocation unit: 256 per warp
                 warps = -(-(threads // 32) // 4) * 4          # warps are allocated in groups of 4 (one per SM sub-partition)
                 assert per_warp * warps <= 65536, (name, regs, threads)

@@ -66,28 +66,41 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_frame_sharded_sample_matches_single_gpu():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _run_world(world: int):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29700 + (os.getpid() + 17 * world) % 1000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    outs = [q.get(timeout=600) for _ in procs]
+    outs = [q.get(timeout=900) for _ in procs]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     ref = torch.from_numpy(golden("sampler_tiny_cfg")["sample"])
     for rank, single, frames, split in outs:
         single = torch.from_numpy(single)
-        print(f"rank {rank}: single-vs-reference {rel_l2(single, ref):.3e}")
+        print(f"[W={world}] rank {rank}: single-vs-reference {rel_l2(single, ref):.3e}")
         for name, arr in (("frames", frames), ("split", split)):
             sharded = torch.from_numpy(arr)
             r1, r2 = rel_l2(sharded, single), rel_l2(sharded, ref)
-            print(f"rank {rank}: {name}-vs-single {r1:.3e}, {name}-vs-reference {r2:.3e}")
+            print(f"[W={world}] rank {rank}: {name}-vs-single {r1:.3e}, {name}-vs-reference {r2:.3e}")
             assert r1 < 3e-3 and r2 < 5e-3
-    assert np.array_equal(outs[0][2], outs[1][2]), "every rank must hold the same gathered latent"
-    assert np.array_equal(outs[0][3], outs[1][3]), "every rank must hold the same latent (CFG split)"
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][2], o[2]), "every rank must hold the same gathered latent"
+        assert np.array_equal(outs[0][3], o[3]), "every rank must hold the same latent (CFG split)"
+
+
+def test_two_gpu_sharded_sample_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_world(2)
+
+
+def test_four_gpu_sharded_sample_matches_single_gpu():
+    """4 ranks: `frames` has interior ranks (both halo neighbours), `split` runs 2 frame shards inside each CFG half
+    (sub-group collectives + the pairwise exchange)."""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run_world(4)

@@ -88,6 +88,17 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+// XOR key of the staging swizzle: 16-byte chunk j of row r sits in slot (j ^ key(r)) mod CH; conflict-free both for
+// the row-per-thread writes and for the RPI-rows-per-instruction reads (CH = 8: 128-byte rows, CH = 4: 64-byte rows).
+template <int CH>
+__device__ __forceinline__ int stage_swz(int row) { return CH == 8 ? row : (row >> 1); }
+
 // Column-group schedule of the two epilogue warpgroups.  G 32-column groups per tile; adjacent groups (2i, 2i+1)
 // form a 128-byte output line and go to the same warpgroup back to back, pairs alternate between the
 // warpgroups; with an odd number of pairs the last pair is split so that both warpgroups get the same load.
@@ -105,9 +116,10 @@ __device__ __forceinline__ int epi_group(int G, int wg, int k) {
   return -1;
 }
 
-// 10 warps are allocated as 12 (granularity 4): 65536 / 384 -> at most 168 registers per thread
-template <int ACT_, bool RV_, int NRES_, bool GEN, bool PAIR>
-__global__ void __launch_bounds__(320, 1)
+// NQ = 2: 10 warps are allocated as 12 (granularity 4): 65536 / 384 -> at most 168 registers per thread.
+// NQ = 4: 18 warps are allocated as 20: the bound is declared as 640 threads so that the compiler stays <= 96.
+template <int ACT_, bool RV_, int NRES_, bool GEN, bool PAIR, int NQ>
+__global__ void __launch_bounds__(NQ == 2 ? 320 : 640, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -136,26 +148,26 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], PAIR ? 16 : 8);   // one arrival per epilogue warp (of both CTAs in a pair)
+      mbar_init(&tempty[i], (PAIR ? 2 : 1) * 4 * NQ);   // one arrival per epilogue warp (of both CTAs in a pair)
     }
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == 4 * NQ && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (PAIR) {
     cluster_sync_all();                       // both CTAs' barriers exist before anything can signal them
-    if (warp == 9) tmem_alloc_pair<512>(tmem_slot);
+    if (warp == 4 * NQ + 1) tmem_alloc_pair<512>(tmem_slot);
   } else {
-    if (warp == 9) tmem_alloc<512>(tmem_slot);
+    if (warp == 4 * NQ + 1) tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 4 * NQ) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -198,7 +210,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 4 * NQ + 1) {
     // ------------------------------------------------------------ MMA issuer (CTA pair: the leader only)
     if (lane == 0 && cta_rank == 0) {
       int stage = 0;
@@ -246,15 +258,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0..7)
-    // Warp w owns TMEM lane quadrant w % 4 (rows 32*(w%4) ..) and the 32-column groups epi_group(G, w/4, .).
-    // Phase A (thread = tile row): tcgen05.ld of the group; GEGLU is evaluated here ((a+ba)*gelu(g+bg)), all other
-    //          epilogues move the raw accumulator; 32 fp32 per row go to the warp's staging buffer (16-byte
+    // ------------------------------------------------------------ epilogue (warps 0 .. 4 NQ - 1)
+    // Warp w owns TMEM lane quadrant w % 4 (rows 32*(w%4) ..) and column groups of CG = 64 / NQ columns:
+    // NQ = 2 (8 warps): 32-column groups dealt out by epi_group(); NQ = 4 (16 warps): 16-column groups, round robin.
+    // Phase A (thread = tile row): tcgen05.ld of the group; GEGLU is evaluated here (value * gelu(gate)), all other
+    //          epilogues move the raw accumulator; CG fp32 per row go to the warp's staging buffer (16-byte
     //          chunks XOR-swizzled by row).
-    // Phase B (lane = 4 fixed columns, 4 rows per instruction): bias / s_acc / row-vector / SiLU / residuals /
+    // Phase B (lane = 4 fixed columns, RPI rows per instruction): bias / s_acc / row-vector / SiLU / residuals /
     //          pack / store; per-column operands are loaded once per group, every global access covers a
-    //          contiguous 64-byte (16-bit) or 128-byte (fp32) row segment.  The first residual is prefetched one
-    //          group ahead (group 0 while the MMAs of the tile still run).
+    //          contiguous row segment of CG output elements.  The first residual is prefetched one group ahead
+    //          (group 0 while the MMAs of the tile still run).
+    constexpr int CG = 64 / NQ;            // columns per group
+    constexpr int CH = CG / 4;             // 16-byte fp32 chunks per staged row
+    constexpr int RPI = 32 / CH;           // rows per phase-B instruction
+    constexpr int NI = 32 / RPI;           // phase-B instructions per group
+    constexpr int MAXK = 4;                // groups per warp and tile (256 / CG / NQ)
     const int act = GEN ? p.act : ACT_;
     const bool has_rv = GEN ? (p.rowvec != nullptr) : RV_;
     const bool has_r1 = GEN ? (p.res1 != nullptr) : (NRES_ >= 1);
@@ -265,16 +283,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aphase = 0;
     const int quad = warp & 3, wg = warp >> 2;
     const int r = quad * 32 + lane;  // row of the tile == TMEM lane
-    const int ch = lane & 7, rsub = lane >> 3;
-    const uint32_t stg = smem_u32(stages + p.nstages * p.stage_bytes) + warp * (32 * 128);
+    const int ch = lane % CH, rsub = lane / CH;
+    const uint32_t stg = smem_u32(stages + p.nstages * p.stage_bytes) + warp * (32 * CG * 4);
     const int half = p.TN >> 1;
     const int tile_out_cols = (act == 2) ? half : p.TN;
     const int n_out_total = (act == 2) ? (p.N >> 1) : p.N;
-    const int G = tile_out_cols >> 5;
+    const int G = tile_out_cols / CG;
     const int out_es = f32o ? 4 : 2;
     const char* r1p = reinterpret_cast<const char*>(p.res1);
     const char* r2p = reinterpret_cast<const char*>(p.res2);
     const bool has_bias = p.bias != nullptr;
+    auto group_of = [&](int k) -> int {
+      if (NQ == 2) return epi_group(G, wg, k);
+      const int g = k * NQ + wg;
+      return g < G ? g : -1;
+    };
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int mq = tile / p.n_tiles, n_blk = tile - mq * p.n_tiles;
       const int m_blk = PAIR ? 2 * mq + (int)cta_rank : mq;
@@ -293,29 +316,29 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         token_own = (b * p.H + h) * p.W + w;
       }
       if (!valid_own) token_own = 0;
-      // rows this lane serves in phase B: row(i) = 4 i + rsub
-      const uint32_t vrows = __ballot_sync(0xffffffffu, valid_own) >> rsub;   // bit 4 i <-> row(i)
-      int tok[8], rvrow[8];
+      // rows this lane serves in phase B: row(i) = RPI i + rsub
+      const uint32_t vrows = __ballot_sync(0xffffffffu, valid_own) >> rsub;   // bit RPI i <-> row(i)
+      int tok[NI], rvrow[NI];
       {
         const int rv_own = has_rv ? (token_own / p.rv_div) % p.rv_mod : 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          tok[i] = __shfl_sync(0xffffffffu, token_own, i * 4 + rsub);
-          rvrow[i] = has_rv ? __shfl_sync(0xffffffffu, rv_own, i * 4 + rsub) : 0;
+        for (int i = 0; i < NI; ++i) {
+          tok[i] = __shfl_sync(0xffffffffu, token_own, i * RPI + rsub);
+          rvrow[i] = has_rv ? __shfl_sync(0xffffffffu, rv_own, i * RPI + rsub) : 0;
         }
       }
       const int n_out_base = n_blk * tile_out_cols;
-      uint2 rpre[2][8];
-      auto prefetch_res = [&](int k, uint2 (&dst)[8]) {
+      uint2 rpre[2][NI];
+      auto prefetch_res = [&](int k, uint2 (&dst)[NI]) {
         if (!has_r1) return;
-        const int g = epi_group(G, wg, k);
-        const int n = n_out_base + g * 32 + ch * 4;
+        const int g = group_of(k);
+        const int n = n_out_base + g * CG + ch * 4;
         const bool ok = (g >= 0) && (n + 4 <= n_out_total);
         const char* base = r1p + (long long)n * 2;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NI; ++i) {
           dst[i] = make_uint2(0, 0);
-          if (ok && ((vrows >> (4 * i)) & 1u)) dst[i] = __ldg(reinterpret_cast<const uint2*>(base + (long long)tok[i] * p.ld_res1_b));
+          if (ok && ((vrows >> (RPI * i)) & 1u)) dst[i] = __ldg(reinterpret_cast<const uint2*>(base + (long long)tok[i] * p.ld_res1_b));
         }
       };
       prefetch_res(0, rpre[0]);
@@ -323,43 +346,43 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int gidx = epi_group(G, wg, k);
+      for (int k = 0; k < MAXK; ++k) {
+        const int gidx = group_of(k);
         if (gidx < 0) break;
-        const int c0 = gidx * 32;
-        if (k + 1 < 4) prefetch_res(k + 1, rpre[(k + 1) & 1]);
+        const int c0 = gidx * CG;
+        if (k + 1 < MAXK) prefetch_res(k + 1, rpre[(k + 1) & 1]);
         if (n_out_base + c0 >= n_out_total) continue;   // group entirely beyond N (last n-tile of a padded N)
         // ---------------- phase A
         if (act != 2) {
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);
+          uint32_t v[CG];
+          tmem_ld_cols<CG>(t_row + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int slot = (j ^ lane) & 7;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + slot * 16), "r"(v[j * 4]),
+          for (int j = 0; j < CH; ++j) {
+            const int slot = (j ^ stage_swz<CH>(lane)) & (CH - 1);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * (CG * 4) + slot * 16), "r"(v[j * 4]),
                          "r"(v[j * 4 + 1]), "r"(v[j * 4 + 2]), "r"(v[j * 4 + 3])
                          : "memory");
           }
         } else {
-          uint32_t va[32], vg[32];
-          tmem_ld32(t_row + c0, va);
-          tmem_ld32(t_row + half + c0, vg);
+          uint32_t va[CG], vg[CG];
+          tmem_ld_cols<CG>(t_row + c0, va);
+          tmem_ld_cols<CG>(t_row + half + c0, vg);
           tmem_ld_wait();
           const int nb = n_blk * p.TN + c0;  // bias index of the value columns (gate: + half)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < CH; ++j) {
             float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_bias) {
               ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j * 4));
               bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + half + j * 4));
             }
-            const float f0 = (__uint_as_float(va[j * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(vg[j * 4 + 0]) + bg.x);
-            const float f1 = (__uint_as_float(va[j * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(vg[j * 4 + 1]) + bg.y);
-            const float f2 = (__uint_as_float(va[j * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(vg[j * 4 + 2]) + bg.z);
-            const float f3 = (__uint_as_float(va[j * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(vg[j * 4 + 3]) + bg.w);
-            const int slot = (j ^ lane) & 7;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + slot * 16), "f"(f0), "f"(f1),
+            const float f0 = geglu_fast(__uint_as_float(va[j * 4 + 0]) + ba.x, __uint_as_float(vg[j * 4 + 0]) + bg.x);
+            const float f1 = geglu_fast(__uint_as_float(va[j * 4 + 1]) + ba.y, __uint_as_float(vg[j * 4 + 1]) + bg.y);
+            const float f2 = geglu_fast(__uint_as_float(va[j * 4 + 2]) + ba.z, __uint_as_float(vg[j * 4 + 2]) + bg.z);
+            const float f3 = geglu_fast(__uint_as_float(va[j * 4 + 3]) + ba.w, __uint_as_float(vg[j * 4 + 3]) + bg.w);
+            const int slot = (j ^ stage_swz<CH>(lane)) & (CH - 1);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * (CG * 4) + slot * 16), "f"(f0), "f"(f1),
                          "f"(f2), "f"(f3)
                          : "memory");
           }
@@ -381,20 +404,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           char* obase = reinterpret_cast<char*>(p.out) + (long long)n * out_es;
           const char* r2base = r2p + (long long)n * 2;
           const char* rvbase = reinterpret_cast<const char*>(p.rowvec) + (long long)n * 4;
-          const uint2(&u1)[8] = rpre[k & 1];
+          const uint2(&u1)[NI] = rpre[k & 1];
 #pragma unroll
-          for (int hb = 0; hb < 2; ++hb) {
+          for (int hb = 0; hb < NI / 4; ++hb) {
             float4 v[4], rv[4];
             uint2 u2[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int i = hb * 4 + q;
-              const int row = i * 4 + rsub;
-              const int slot = (ch ^ row) & 7;
+              const int row = i * RPI + rsub;
+              const int slot = (ch ^ stage_swz<CH>(row)) & (CH - 1);
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                            : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
-                           : "r"(stg + row * 128 + slot * 16));
-              const bool ok = n_ok && ((vrows >> (4 * i)) & 1u);
+                           : "r"(stg + row * (CG * 4) + slot * 16));
+              const bool ok = n_ok && ((vrows >> (RPI * i)) & 1u);
               rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
               u2[q] = make_uint2(0, 0);
               if (has_rv && ok) rv[q] = __ldg(reinterpret_cast<const float4*>(rvbase + (long long)rvrow[i] * p.ld_rowvec_b));
@@ -403,7 +426,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int i = hb * 4 + q;
-              const bool ok = n_ok && ((vrows >> (4 * i)) & 1u);   // straight-line code, predicated store
+              const bool ok = n_ok && ((vrows >> (RPI * i)) & 1u);   // straight-line code, predicated store
               float4 o = v[q];
               if (act != 2) {
                 o.x = fmaf(o.x, sa, bs.x); o.y = fmaf(o.y, sa, bs.y); o.z = fmaf(o.z, sa, bs.z); o.w = fmaf(o.w, sa, bs.w);
@@ -444,7 +467,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncwarp();
   if (PAIR) cluster_sync_all(); else __syncthreads();
-  if (warp == 9) {
+  if (warp == 4 * NQ + 1) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
@@ -555,12 +578,14 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   // Epilogue variant: the common fp16 feature sets are compiled in (no per-element feature tests), everything
   // else (bf16 operands, fp32 output, unusual combinations) takes the generic instantiation.
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const TGParams);
-#define VB_VARIANTS(PAIR)                                                                                         \
-  {tapgemm_kernel<0, false, 0, false, PAIR>, tapgemm_kernel<0, false, 1, false, PAIR>,                            \
-   tapgemm_kernel<0, false, 2, false, PAIR>, tapgemm_kernel<0, true, 0, false, PAIR>,                             \
-   tapgemm_kernel<0, true, 1, false, PAIR>,  tapgemm_kernel<1, false, 0, false, PAIR>,                            \
-   tapgemm_kernel<2, false, 0, false, PAIR>, tapgemm_kernel<0, true, 2, true, PAIR>}
-  static const Kern kVariants[2][8] = {VB_VARIANTS(false), VB_VARIANTS(true)};
+#define VB_VARIANTS(PAIR, NQ)                                                                                     \
+  {tapgemm_kernel<0, false, 0, false, PAIR, NQ>, tapgemm_kernel<0, false, 1, false, PAIR, NQ>,                    \
+   tapgemm_kernel<0, false, 2, false, PAIR, NQ>, tapgemm_kernel<0, true, 0, false, PAIR, NQ>,                     \
+   tapgemm_kernel<0, true, 1, false, PAIR, NQ>,  tapgemm_kernel<1, false, 0, false, PAIR, NQ>,                    \
+   tapgemm_kernel<2, false, 0, false, PAIR, NQ>, tapgemm_kernel<0, true, 2, true, PAIR, NQ>}
+  // [pair][16 epilogue warps]: the CTA-pair kernel exists with 8 epilogue warps only
+  static const Kern kVariants[2][2][8] = {{VB_VARIANTS(false, 2), VB_VARIANTS(false, 4)},
+                                          {VB_VARIANTS(true, 2), VB_VARIANTS(true, 2)}};
 #undef VB_VARIANTS
   int variant = 7;
   if (!d->bf16 && !d->out_f32 && !getenv("VB_GEMM_GENERIC")) {
@@ -570,12 +595,20 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     else if (d->act == 1 && !d->rowvec && nres == 0) variant = 5;
     else if (d->act == 2) variant = 6;
   }
+  // 16 epilogue warps (4 per scheduler) hide the MUFU / dependency latency of the GEGLU epilogue; the light
+  // epilogues keep 8 warps and 32-column groups (fewer per-group fixed costs).  VB_GEMM_NQ=2|4 forces one.
+  static const int nq_force = getenv("VB_GEMM_NQ") ? atoi(getenv("VB_GEMM_NQ")) : 0;
+  int wide = (variant == 6) ? 1 : 0;
+  if (nq_force == 2) wide = 0;
+  if (nq_force == 4) wide = 1;
+  if (pair) wide = 0;
   static bool attr_set = false;
   static int max_clusters = 0;
   if (!attr_set) {
     for (int q = 0; q < 2; ++q)
-      for (int i = 0; i < 8; ++i)
-        VB_CHECK_CUDA(cudaFuncSetAttribute(kVariants[q][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      for (int w = 0; w < 2; ++w)
+        for (int i = 0; i < 8; ++i)
+          VB_CHECK_CUDA(cudaFuncSetAttribute(kVariants[q][w][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // how many CTA pairs the device runs at once (pairs sit on the two SMs of a TPC)
     cudaLaunchConfig_t qc = {};
     cudaLaunchAttribute qa[1];
@@ -583,7 +616,7 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.gridDim = dim3(2 * device_sm_count()); qc.blockDim = dim3(320); qc.dynamicSmemBytes = 227 * 1024;
     qc.attrs = qa; qc.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kVariants[1][0], &qc) != cudaSuccess || max_clusters <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kVariants[1][0][0], &qc) != cudaSuccess || max_clusters <= 0) {
       cudaGetLastError();
       max_clusters = device_sm_count() / 2;
     }
@@ -599,12 +632,12 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kVariants[1][variant], tmA, tmB, p));
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kVariants[1][0][variant], tmA, tmB, p));
   } else {
     const long long total = (long long)p.m_tiles * p.n_tiles;
     int grid = device_sm_count();
     if (total < grid) grid = (int)total;
-    kVariants[0][variant]<<<grid, 320, smem_bytes, stream>>>(tmA, tmB, p);
+    kVariants[0][wide][variant]<<<grid, wide ? 576 : 320, smem_bytes, stream>>>(tmA, tmB, p);
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;

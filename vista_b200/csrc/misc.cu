@@ -39,18 +39,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 // floating-point atomics, no memset (the counter resets itself).
 // ------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
+constexpr int kGnMaxJ = 4;  // max vectors per thread (C <= 8 * 256 * kGnMaxJ); kernels are templated on 1 / 2 / 4
 constexpr int kGnMinChunk = 16;   // b200v_groupnorm_chunk(): lower bound of the tokens one block walks
-// Tokens per block: about 8 blocks per SM over the whole launch (small feature maps would otherwise leave most
-// SMs idle), a multiple of 8, within [kGnMinChunk, 256].  A pure function of the shape: results stay
-// bit-reproducible from run to run.
+// Tokens per block: about 16 blocks per SM over the whole launch (small feature maps would otherwise leave most
+// SMs idle; huge ones would leave the last block of a statistic tens of thousands of partial sums to add), a
+// multiple of 8, at least kGnMinChunk.  A pure function of the shape: results stay bit-reproducible.
 static inline int gn_pick_chunk(int frames, int tokens_per_frame) {
-  long long c = ((long long)frames * tokens_per_frame + 1183) / 1184;
+  long long c = ((long long)frames * tokens_per_frame + 2367) / 2368;
   c = (c + 7) / 8 * 8;
   if (c < kGnMinChunk) c = kGnMinChunk;
-  if (c > 256) c = 256;
+  if (c > tokens_per_frame) c = (tokens_per_frame + 7) / 8 * 8;
   return (int)c;
 }
-constexpr int kGnMaxJ = 4;  // max vectors per thread (C <= 8 * 256 * kGnMaxJ); kernels are templated on 1 / 2 / 4
 
 template <int JT>
 __global__ void __launch_bounds__(kGnThreads)
