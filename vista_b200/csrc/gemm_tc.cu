@@ -183,7 +183,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int w0 = tw * p.BW, h0 = th * p.BH, b0 = tb * p.BB;
         const int n0 = n_blk * p.TN + (PAIR ? (int)cta_rank * b_rows : 0);
         for (int kc = 0; kc < KC; ++kc) {
-          mbar_wait(&empty[stage], phase ^ 1, 1);
+          mbar_wait_relaxed(&empty[stage], phase ^ 1, 1);
           uint8_t* sA = stages + stage * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
           const int tap = kc / p.kc_per_tap;
@@ -227,7 +227,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t b_off = kABytes >> 4;
       uint32_t a_lo = a_lo0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-        mbar_wait(&tempty[as], aphase ^ 1, 2);
+        mbar_wait_relaxed(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
         for (int kc = 0; kc < KC; ++kc) {
@@ -365,25 +365,46 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                          : "memory");
           }
         } else {
+          // bias of the group's value | gate columns: one coalesced load per lane, broadcast through the (idle)
+          // staging buffer instead of 2 CG / 4 uniform loads with their address arithmetic in every thread
+          const int nb = n_blk * p.TN + c0;  // bias index of the value columns (gate: + half)
+          if (has_bias) {
+            float bv = 0.f;
+            if (lane < 2 * CG || CG == 32) {
+              if (CG == 32) {
+                const float b0 = __ldg(p.bias + nb + lane), b1 = __ldg(p.bias + nb + half + lane);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + lane * 4), "f"(b0) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + (CG + lane) * 4), "f"(b1) : "memory");
+              } else {
+                bv = __ldg(p.bias + nb + (lane < CG ? lane : half + lane - CG));
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + lane * 4), "f"(bv) : "memory");
+              }
+            }
+            __syncwarp();
+          }
           uint32_t va[CG], vg[CG];
           tmem_ld_cols<CG>(t_row + c0, va);
           tmem_ld_cols<CG>(t_row + half + c0, vg);
-          tmem_ld_wait();
-          const int nb = n_blk * p.TN + c0;  // bias index of the value columns (gate: + half)
+          float f[CG];
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_bias) {
-              ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j * 4));
-              bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + half + j * 4));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ba.x), "=f"(ba.y), "=f"(ba.z), "=f"(ba.w) : "r"(stg + j * 16));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bg.x), "=f"(bg.y), "=f"(bg.z), "=f"(bg.w) : "r"(stg + (CG + j * 4) * 4));
             }
-            const float f0 = geglu_fast(__uint_as_float(va[j * 4 + 0]) + ba.x, __uint_as_float(vg[j * 4 + 0]) + bg.x);
-            const float f1 = geglu_fast(__uint_as_float(va[j * 4 + 1]) + ba.y, __uint_as_float(vg[j * 4 + 1]) + bg.y);
-            const float f2 = geglu_fast(__uint_as_float(va[j * 4 + 2]) + ba.z, __uint_as_float(vg[j * 4 + 2]) + bg.z);
-            const float f3 = geglu_fast(__uint_as_float(va[j * 4 + 3]) + ba.w, __uint_as_float(vg[j * 4 + 3]) + bg.w);
+            if (j == 0) tmem_ld_wait();
+            f[j * 4 + 0] = geglu_fast(__uint_as_float(va[j * 4 + 0]) + ba.x, __uint_as_float(vg[j * 4 + 0]) + bg.x);
+            f[j * 4 + 1] = geglu_fast(__uint_as_float(va[j * 4 + 1]) + ba.y, __uint_as_float(vg[j * 4 + 1]) + bg.y);
+            f[j * 4 + 2] = geglu_fast(__uint_as_float(va[j * 4 + 2]) + ba.z, __uint_as_float(vg[j * 4 + 2]) + bg.z);
+            f[j * 4 + 3] = geglu_fast(__uint_as_float(va[j * 4 + 3]) + ba.w, __uint_as_float(vg[j * 4 + 3]) + bg.w);
+          }
+          __syncwarp();                              // every lane has read the bias before the buffer is reused
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
             const int slot = (j ^ stage_swz<CH>(lane)) & (CH - 1);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * (CG * 4) + slot * 16), "f"(f0), "f"(f1),
-                         "f"(f2), "f"(f3)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * (CG * 4) + slot * 16), "f"(f[j * 4]),
+                         "f"(f[j * 4 + 1]), "f"(f[j * 4 + 2]), "f"(f[j * 4 + 3])
                          : "memory");
           }
         }
@@ -595,10 +616,10 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     else if (d->act == 1 && !d->rowvec && nres == 0) variant = 5;
     else if (d->act == 2) variant = 6;
   }
-  // 16 epilogue warps (4 per scheduler) hide the MUFU / dependency latency of the GEGLU epilogue; the light
-  // epilogues keep 8 warps and 32-column groups (fewer per-group fixed costs).  VB_GEMM_NQ=2|4 forces one.
+  // 16 epilogue warps (4 per scheduler) hide the MUFU / dependency latency of the small-K GEGLU epilogue; everything
+  // else keeps 8 warps and 32-column groups (fewer per-group fixed costs).  VB_GEMM_NQ=2|4 forces one.
   static const int nq_force = getenv("VB_GEMM_NQ") ? atoi(getenv("VB_GEMM_NQ")) : 0;
-  int wide = (variant == 6) ? 1 : 0;
+  int wide = (variant == 6 && K <= 384) ? 1 : 0;   // measured: L0 GEGLU (K = 320) 0.91 vs 0.94 ms, K = 640 the other way
   if (nq_force == 2) wide = 0;
   if (nq_force == 4) wide = 1;
   if (pair) wide = 0;

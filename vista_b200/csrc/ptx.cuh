@@ -60,6 +60,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     }
   }
 }
+// Same, for waits that are usually long (a producer ahead of its consumer, an issuer behind a slow epilogue): after a
+// few failed probes the warp sleeps between probes instead of burning the issue slots the epilogue warps need.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int tag = 0) {
+  for (int i = 0; i < 4; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  long long t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    __nanosleep(32);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 4095u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > VB_WAIT_TIMEOUT_CYCLES) {
+        printf("vista_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
+               blockIdx.y, blockIdx.z, threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -73,6 +73,10 @@ class DiffusionEngine(nn.Module):
         dec = self.first_stage_model.decoder
         if not isinstance(dec, VideoDecoder):
             raise NotImplementedError("decode_first_stage needs vista_b200.vae.VideoDecoder as decoder_config.target")
+        if getattr(self.model, "frame_sharded", False):     # one clip on several ranks: deal the chunks out as well
+            from .vae import decode_first_stage_parallel
+            return decode_first_stage_parallel(dec.runtime(z.device), z, self.scale_factor,
+                                               self.en_and_decode_n_samples_a_time, overlap)
         return _decode_first_stage(dec.runtime(z.device), z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap)
 
     def encode_first_stage(self, x):
