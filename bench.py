@@ -308,7 +308,12 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # The measurement is complete and printed.  Leave without the NCCL / interpreter teardown: a multi-rank process
+        # that lingers there (observed once after a taped frame-sharded run) would hold the whole launch hostage.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -397,6 +402,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1 if args.impl == "reference" else 3)
+    if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        # multi-rank watchdog: a rank that is still here after 15 minutes is stuck in a collective; exit non-zero
+        # instead of blocking the launcher until its own timeout
+        t = threading.Timer(900.0, lambda: (sys.stderr.write("bench.py: watchdog expired, aborting rank\n"), sys.stderr.flush(), os._exit(3)))
+        t.daemon = True
+        t.start()
     if args.impl == "reference":
         return run_reference(args)
     run_ours(args)

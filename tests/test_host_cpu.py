@@ -218,3 +218,25 @@ def test_engine_from_yaml_config_exposes_reference_state_dict_keys():
         eng.encode_first_stage(torch.zeros(1, 3, 8, 8))
     from vista_b200.diffusion import EulerEDMSampler, VanillaCFG
     assert isinstance(eng.sampler, EulerEDMSampler) and isinstance(eng.sampler.guider, VanillaCFG)
+
+
+def test_launch_tape_records_and_replays_in_order():
+    """vista_b200.lib launch tape: C-ABI calls issued through the recording proxy and host-side operations
+    (collectives) are replayed in their original order; a failing replayed call raises."""
+    from vista_b200 import lib
+    log = []
+    lib.begin_tape()
+    assert lib.taping()
+    l = lib.load()                                   # recording proxy while a tape is open
+    assert l.b200v_groupnorm_chunk() >= 8            # queries are not recorded
+    lib.tape_host(lambda: log.append("h1"))
+    rc = l.b200v_layernorm(None, 8, None, 8, 1, 8, None, None, 1e-5, None, 0, 1, 1, None)    # null pointers: rc != 0, no launch
+    assert rc != 0
+    lib.tape_host(lambda: log.append("h2"))
+    tape = lib.end_tape()
+    assert not lib.taping() and len(tape) == 3 and log == ["h1", "h2"]
+    with pytest.raises(RuntimeError):                # the recorded failing call fails again on replay, after h1
+        lib.replay(tape)
+    assert log == ["h1", "h2", "h1"]
+    lib.replay([tape[0], tape[2]])
+    assert log == ["h1", "h2", "h1", "h1", "h2"]

@@ -16,10 +16,12 @@ from typing import Dict, Optional
 
 import torch
 
+from . import lib as _lib
 from . import ops
 from .unet import padded_input_rows
 
 USE_GRAPH = os.environ.get("VISTA_B200_GRAPH", "1") != "0"
+USE_TAPE = os.environ.get("VISTA_B200_TAPE", "1") != "0"     # launch-tape replay of steps that hold collectives
 
 
 class _LoopState:
@@ -42,6 +44,7 @@ class _LoopState:
         self.unet_in = padded_input_rows(2 * N * h * w, dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_steps = None
+        self.tape, self.tape_steps = None, None      # launch tape of one step (frame-sharded runtimes)
         # CFG-split mode (modules.enable_frame_sharding): this rank runs one half of the doubled batch
         self.split = None            # (half, pair process group)
         self.net_full = None         # [2 N h w, 8] fp32: both halves' network outputs after the pair exchange
@@ -67,8 +70,9 @@ class _LoopState:
     def _finish(self, net_out, num_steps: int):
         if self.split is not None:                # guidance needs both halves of the frames this rank owns
             import torch.distributed as dist
-            dist.all_gather_into_tensor(self.net_full, net_out, group=self.split[1])
-            net_out = self.net_full
+            full, pg = self.net_full, self.split[1]
+            _lib.tape_host(lambda: dist.all_gather_into_tensor(full, net_out, group=pg))
+            net_out = full
         ops.sampler_update(self.x, net_out, self.cond_frame, self.mask, self.scales, self.sigmas, self.step,
                            num_steps, self.N, self.h, self.w)
 
@@ -80,8 +84,24 @@ class _LoopState:
         """Callable advancing one step the fastest supported way; call after one eager step (which allocates every
         buffer of the executor).  Without a collective inside the UNet the launch sequence is replayed from a CUDA
         graph: the whole step, or prepare + UNet in CFG-split mode (the pair exchange and the update stay eager)."""
-        if not USE_GRAPH or getattr(rt, "group", None) is not None:
+        if not USE_GRAPH:
             return lambda: self.one_step(rt, num_steps)
+        if getattr(rt, "group", None) is not None and not USE_TAPE:
+            return lambda: self.one_step(rt, num_steps)
+        if getattr(rt, "group", None) is not None:
+            # collectives inside the UNet: no graph; the first call records the step's C-ABI calls and host-side
+            # collectives on a launch tape (vista_b200.lib), later calls replay it without the Python layers above
+            def run_taped():
+                if self.tape is None or self.tape_steps != num_steps:
+                    _lib.begin_tape()
+                    try:
+                        self.one_step(rt, num_steps)
+                    finally:
+                        tape = _lib.end_tape()
+                    self.tape, self.tape_steps = tape, num_steps
+                else:
+                    _lib.replay(self.tape)
+            return run_taped
         if self.graph is None or self.graph_steps != num_steps:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()

@@ -126,7 +126,7 @@ def load() -> C.CDLL:
     """dlopen the in-tree library (must have been built); binds all signatures."""
     global _lib
     if _lib is not None:
-        return _lib
+        return _lib if _tape is None else _Recorder(_lib)
     if not os.path.isfile(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no fallback path)")
@@ -139,6 +139,62 @@ def load() -> C.CDLL:
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Launch tape.  The executor issues the same C-ABI calls with the same arguments every sampler step (all buffers are
+# persistent), so one recorded step can be replayed without the Python logic above it: `begin_tape()` makes `load()`
+# hand out a recording proxy, `end_tape()` returns [(callable, args)]; host-side operations that must stay in order
+# with the kernels (torch.distributed collectives, tensor copies) are added with `tape_host()`.  Used where a CUDA
+# graph is not (the frame-sharded step with its NCCL calls); the same stability rules as for graph capture apply.
+# ---------------------------------------------------------------------------------------------------------------
+_tape: Optional[list] = None
+_NO_TAPE = {"b200v_groupnorm_chunk", "b200v_groupnorm_chunk_for", "b200v_version", "b200v_device_info", "b200v_last_error"}
+
+
+class _Recorder:
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name in _NO_TAPE:
+            return fn
+
+        def call(*args):
+            if _tape is not None:
+                _tape.append((fn, args))
+            return fn(*args)
+        return call
+
+
+def begin_tape():
+    global _tape
+    _tape = []
+
+
+def end_tape() -> list:
+    global _tape
+    t, _tape = _tape, None
+    return t
+
+
+def taping() -> bool:
+    return _tape is not None
+
+
+def tape_host(fn):
+    """Run a host-side operation now and, while a tape is being recorded, put it on the tape."""
+    if _tape is not None:
+        _tape.append((fn, ()))
+    return fn()
+
+
+def replay(tape: list):
+    for fn, args in tape:
+        rc = fn(*args)
+        if type(rc) is int and rc != 0:
+            check(rc, "replayed call")
 
 
 def check(rc: int, what: str = ""):

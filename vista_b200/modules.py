@@ -13,6 +13,7 @@ Both fail loudly without the CUDA library or a CUDA device: there is no CPU / ea
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Union
 
 import torch
@@ -102,7 +103,7 @@ class _RuntimeOwner:
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if cfg_split is None:
-            cfg_split = world % 2 == 0
+            cfg_split = world % 2 == 0 and os.environ.get("VISTA_B200_CFG_SPLIT", "1") != "0"
         self.frame_sharded = True
         self.cfg_half, self.pair_group = None, None
         if cfg_split:

@@ -28,6 +28,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
+from . import lib as _lib
 from . import ops
 from .parallel import frame_shards, halo_neighbours
 from .spec import UNetConfig
@@ -83,7 +84,7 @@ class ShardedUNetRuntime(UNetRuntime):
         Cc = norm[0].numel()
         sums = self.buf(f"gn.sums{nb}", nb * self.cfg.num_groups, 2, torch.float64)
         ops.groupnorm_sums(x, B, hw, Cc, sums, fps, groups=self.cfg.num_groups, ws=self.gn_ws)
-        dist.all_reduce(sums, group=self.group)
+        _lib.tape_host(lambda: dist.all_reduce(sums, group=self.group))
         self.comm_bytes += sums.numel() * 8
         count = float(Cc // self.cfg.num_groups) * hw * self.T_full
         return ops.groupnorm_finalize_apply(x, y, B, hw, norm[0], norm[1], eps, silu, sums, count,
@@ -108,20 +109,30 @@ class ShardedUNetRuntime(UNetRuntime):
         recv_next = self.buf("halo.rn", nb * hw, Cc)
         a4 = a.reshape(nb, T, hw, Cc) if a.is_contiguous() else None
         av = a4 if a4 is not None else a.as_strided((nb, T, hw, Cc), (T * hw * a.stride(0), hw * a.stride(0), a.stride(0), 1))
-        p2p = []
+        p2p, copies = [], []
         if self.prev is not None:
-            send_first.view(nb, hw, Cc).copy_(av[:, 0])
+            copies.append((send_first.view(nb, hw, Cc), av[:, 0]))
             p2p.append(dist.P2POp(dist.isend, send_first, self.prev, self.group))
             p2p.append(dist.P2POp(dist.irecv, recv_prev, self.prev, self.group))
         if self.next is not None:
-            send_last.view(nb, hw, Cc).copy_(av[:, T - 1])
+            copies.append((send_last.view(nb, hw, Cc), av[:, T - 1]))
             p2p.append(dist.P2POp(dist.isend, send_last, self.next, self.group))
             p2p.append(dist.P2POp(dist.irecv, recv_next, self.next, self.group))
-        reqs = dist.batch_isend_irecv(p2p) if p2p else []
+        pending = []
+
+        def start_halo():                  # host-side step, replayable (vista_b200.lib launch tape)
+            for dst, src in copies:
+                dst.copy_(src)
+            pending[:] = dist.batch_isend_irecv(p2p) if p2p else []
+
+        def wait_halo():
+            for r in pending:
+                r.wait()
+            pending.clear()
+        _lib.tape_host(start_halo)
         self.comm_bytes += 2 * nb * hw * Cc * 2 * ((self.prev is not None) + (self.next is not None))
         self.gemm(a, lin, out, taps=ops.TAPS_T3, geom=(hw, T, nb), **epi)
-        for r in reqs:
-            r.wait()
+        _lib.tape_host(wait_halo)
         s_acc = epi.get("s_acc", 1.0)
         w0, w2 = self._tap_weights(lin)
         ov = out.as_strided((nb, T, hw, out.shape[1]), (T * hw * out.stride(0), hw * out.stride(0), out.stride(0), 1))
@@ -155,8 +166,9 @@ class ShardedUNetRuntime(UNetRuntime):
         recv = self.buf("kv.recv", W * nb * Tp * hw, 2 * Cc)
         kv = qkv[:, Cc:].reshape(nb, T, hw, 2 * Cc) if False else qkv.as_strided(
             (nb, T, hw, 2 * Cc), (T * hw * qkv.stride(0), hw * qkv.stride(0), qkv.stride(0), 1), qkv.storage_offset() + Cc)
-        send.view(nb, Tp, hw, 2 * Cc)[:, :T].copy_(kv)
-        dist.all_gather_into_tensor(recv, send, group=self.group)
+        dst = send.view(nb, Tp, hw, 2 * Cc)[:, :T]
+        _lib.tape_host(lambda: dst.copy_(kv))
+        _lib.tape_host(lambda: dist.all_gather_into_tensor(recv, send, group=self.group))
         self.comm_bytes += recv.numel() * 2
         tab = self._frame_table(nb, hw)
         return ops.attention_temporal_sharded(qkv[:, :Cc], recv[:, :Cc], recv[:, Cc:], o, nb, T, self.T_full, hw, heads, tab)
