@@ -239,30 +239,57 @@ gn_apply_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// LayerNorm: a warp normalises TPW consecutive tokens; the rows live in registers (NV 16-byte vectors per lane and
-// token), all TPW x NV loads are issued before the first reduction (bytes in flight), gamma / beta are loaded once
-// per warp, two-pass statistics.  Templated on NV so that the common widths (C = 320: NV 2, 640: 3, 1280: 5) keep the
-// register count low (the kernel is a pure HBM stream).
+// LayerNorm: one warp per token, the row lives in registers (NV 16-byte vectors per lane), two-pass
+// statistics.  Templated on NV so that the common widths (C = 320: NV 2, 640: 3, 1280: 5) keep the
+// register count low and the SM full of warps (the kernel is a pure HBM stream).
 // ------------------------------------------------------------------------------------------
-template <int NV, int TPW>
+template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, long long tokens,
                  int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  const float* __restrict__ addvec, long long ld_addvec, int av_div, int av_mod) {
   const int lane = threadIdx.x & 31;
-  const long long token0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW;
-  if (token0 >= tokens) return;
+  const long long token = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (token >= tokens) return;
   const int nvec = C >> 3;
-  uint4 raw[TPW][NV];
+  uint4 raw[NV];
 #pragma unroll
-  for (int t = 0; t < TPW; ++t)
+  for (int j = 0; j < NV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) raw[j] = __ldg(reinterpret_cast<const uint4*>(x + token * ldx + vi * 8));
+  }
+  float v[NV][8];
+  const float* av = addvec ? addvec + ((token / av_div) % av_mod) * ld_addvec : nullptr;
+  float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int vi = lane + j * 32;
-      raw[t][j] = make_uint4(0, 0, 0, 0);
-      if (vi < nvec && token0 + t < tokens) raw[t][j] = __ldg(reinterpret_cast<const uint4*>(x + (token0 + t) * ldx + vi * 8));
+  for (int j = 0; j < NV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      h8_to_f(raw[j], v[j]);
+      if (av) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8 + 4));
+        v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
+        v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[j][i];
     }
-  float gg[NV][8], bb[NV][8];
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[j][i] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int vi = lane + j * 32;
@@ -271,57 +298,12 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-      gg[j][0] = g0.x; gg[j][1] = g0.y; gg[j][2] = g0.z; gg[j][3] = g0.w;
-      gg[j][4] = g1.x; gg[j][5] = g1.y; gg[j][6] = g1.z; gg[j][7] = g1.w;
-      bb[j][0] = b0.x; bb[j][1] = b0.y; bb[j][2] = b0.z; bb[j][3] = b0.w;
-      bb[j][4] = b1.x; bb[j][5] = b1.y; bb[j][6] = b1.z; bb[j][7] = b1.w;
-    }
-  }
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
 #pragma unroll
-  for (int t = 0; t < TPW; ++t) {
-    const long long token = token0 + t;
-    if (token >= tokens) break;
-    float v[NV][8];
-    const float* av = addvec ? addvec + ((token / av_div) % av_mod) * ld_addvec : nullptr;
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int vi = lane + j * 32;
-      if (vi < nvec) {
-        h8_to_f(raw[t][j], v[j]);
-        if (av) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8 + 4));
-          v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
-          v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sum += v[j][i];
-      }
-    }
-    const float mean = warp_sum(sum) / (float)C;
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int vi = lane + j * 32;
-      if (vi < nvec) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float d = v[j][i] - mean;
-          sq += d * d;
-        }
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int vi = lane + j * 32;
-      if (vi < nvec) {
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * gg[j][i] + bb[j][i];
-        *reinterpret_cast<uint4*>(y + token * ldy + vi * 8) = f_to_h8(o);
-      }
+      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * gg[i] + bb[i];
+      *reinterpret_cast<uint4*>(y + token * ldy + vi * 8) = f_to_h8(o);
     }
   }
 }
@@ -878,16 +860,17 @@ extern "C" int b200v_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy,
   VB_REQUIRE(C % 8 == 0 && C <= 2560 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm: C=%d unsupported", C);
   VB_REQUIRE(!addvec || (av_div > 0 && av_mod > 0 && ld_addvec % 4 == 0), "layernorm: bad addvec args");
   const int wpb = 8;
+  const unsigned grid = (unsigned)((tokens + wpb - 1) / wpb);
   const int nv = (C / 8 + 31) / 32;
   const int ad = av_div > 0 ? av_div : 1, am = av_mod > 0 ? av_mod : 1;
-#define VB_LN_LAUNCH(NV, TPW)                                                                                        \
-  layernorm_kernel<NV, TPW><<<(unsigned)((tokens + wpb * TPW - 1) / (wpb * TPW)), wpb * 32, 0, (cudaStream_t)stream>>>( \
-      (const __half*)x, ldx, (__half*)y, ldy, tokens, C, gamma, beta, eps, addvec, ld_addvec, ad, am)
-  if (nv <= 1) VB_LN_LAUNCH(1, 4);
-  else if (nv <= 2) VB_LN_LAUNCH(2, 4);
-  else if (nv <= 3) VB_LN_LAUNCH(3, 2);
-  else if (nv <= 5) VB_LN_LAUNCH(5, 1);
-  else VB_LN_LAUNCH(10, 1);
+#define VB_LN_LAUNCH(NV)                                                                                             \
+  layernorm_kernel<NV><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, tokens, C, \
+                                                                     gamma, beta, eps, addvec, ld_addvec, ad, am)
+  if (nv <= 1) VB_LN_LAUNCH(1);
+  else if (nv <= 2) VB_LN_LAUNCH(2);
+  else if (nv <= 3) VB_LN_LAUNCH(3);
+  else if (nv <= 5) VB_LN_LAUNCH(5);
+  else VB_LN_LAUNCH(10);
 #undef VB_LN_LAUNCH
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
