@@ -240,3 +240,34 @@ def test_launch_tape_records_and_replays_in_order():
     assert log == ["h1", "h2", "h1"]
     lib.replay([tape[0], tape[2]])
     assert log == ["h1", "h2", "h1", "h1", "h2"]
+
+
+def test_decode_chunk_plan_matches_reference_loop():
+    """vae._decode_chunks restates the chunk walk of DiffusionEngine.decode_first_stage (vwm/models/diffusion.py:150-180):
+    context = previous `overlap` frames + the next n_samples - overlap frames, written at pos - overlap, the first
+    `overlap` frames of every chunk but the first averaged with what is there."""
+    from vista_b200.vae import _decode_chunks
+
+    def reference_walk(F, n_samples, overlap):
+        frames = list(range(F))
+        out = []
+        if overlap < n_samples:
+            prev, pos, first = frames[:overlap], overlap, True
+            rest = frames[overlap:]
+            step = n_samples - overlap
+            for i in range(0, len(rest), step):
+                cur = rest[i:i + step]
+                ctx = prev + cur
+                prev = cur[-overlap:]
+                out.append((ctx[0], len(ctx), pos - overlap, 0 if first else overlap))
+                pos += len(cur)
+                first = False
+        else:
+            for i in range(0, F, n_samples):
+                cur = frames[i:i + n_samples]
+                out.append((cur[0], len(cur), i, 0))
+        return out
+
+    for F, n, ov in [(25, 14, 3), (25, 25, 3), (8, 4, 1), (14, 14, 3), (30, 14, 3), (5, 2, 3)]:
+        assert _decode_chunks(F, n, ov) == reference_walk(F, n, ov), (F, n, ov)
+    assert _decode_chunks(25, 14, 3) == [(0, 14, 0, 0), (11, 14, 11, 3)]

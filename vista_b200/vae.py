@@ -204,6 +204,9 @@ def _decode_chunks(F_: int, n_samples: int, overlap: int):
     """Chunk plan of decode_first_stage (vwm/models/diffusion.py:150-180): (first input frame, frame count,
     first output frame, overlapping frames that are averaged with the previous chunk's output)."""
     chunks = []
+    if overlap == 0 and n_samples < F_:
+        # previous_z = current_z[-0:] is the WHOLE previous chunk in the reference (diffusion.py:178): not a usable mode
+        raise NotImplementedError("decode_first_stage: overlap = 0 with more than one chunk is ill-defined in the reference")
     if overlap < n_samples:
         pos, first, prev_len = overlap, True, overlap
         while pos < F_:
