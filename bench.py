@@ -302,7 +302,7 @@ def run_ours(args):
                        "step": {"achieved": ach, "frac": (ach / peaks["tflops"]) if ach else None, "flops_per_step_T": F_STEP_TFLOP,
                                 "scope": "153.9 algorithmic TFLOP of the UNet step / step time (all kernels)"},
                        "families": gemm_prof,
-                       "traffic_note": "ncu dram bytes per launch for the L0 shapes are in profiles/r01_ncu_full_summary.md"}
+                       "traffic_note": "ncu dram bytes per launch (= algorithmic bytes: 554 vs 592 MB conv3x3 L0, 1425 vs 1476 MB GEGLU L0) are in profiles/r01_ncu_full_summary_v2.md; null here because the roofline aggregates 307 launches of many shapes"}
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     if rank == 0:

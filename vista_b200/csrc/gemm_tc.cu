@@ -1,8 +1,9 @@
-// Tap-GEMM: persistent, warp-specialised tcgen05 kernel.
-//   warp 8 : TMA producer  (A tile 128 tokens x 64 ch per tap / K-chunk, B tile tile_n x 64)
-//   warp 9 : TMEM owner + single-thread tcgen05.mma issuer (M=128, N=tile_n, K=16 per instruction)
-//   warps 0-7 : epilogue, two per TMEM lane quadrant (tcgen05.ld -> fused bias / row-vector / activation /
-//               GEGLU -> smem transpose -> coalesced residual loads and stores)
+// Tap-GEMM: persistent, warp-specialised tcgen05 kernel (template tapgemm_kernel<ACT, RV, NRES, GEN, PAIR, NQ>).
+//   warps 0 .. 4 NQ - 1 : epilogue, NQ (2 or 4) per TMEM lane quadrant (tcgen05.ld -> smem transpose -> fused bias /
+//                         row-vector / SiLU / GEGLU / residuals -> coalesced stores)
+//   warp 4 NQ           : TMA producer  (A tile 128 tokens x 64 ch per tap / K-chunk, B tile tile_n x 64)
+//   warp 4 NQ + 1       : TMEM owner + single-thread tcgen05.mma issuer (M=128, N=tile_n, K=16 per instruction;
+//                         PAIR: cta_group::2, M=256 over the two CTAs of a cluster)
 // Two accumulator stages in TMEM (2 x 256 columns) let the epilogue of tile i overlap the MMAs of
 // tile i+1.  The 3x3 / (3,1,1) convolutions are implicit GEMMs: the A tile of every tap is a
 // shifted 4-D TMA box of the token-major activation, zero padding comes from TMA OOB fill.
@@ -44,36 +45,6 @@ struct TGParams {
   float s_res2;
   float s_acc;
 };
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int bf16) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (bf16) {
-      f[2 * i] = __uint_as_float(w[i] << 16);
-      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    } else {
-      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
-      float2 t = __half22float2(h);
-      f[2 * i] = t.x;
-      f[2 * i + 1] = t.y;
-    }
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf16) {
-  uint32_t w[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (bf16) {
-      __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&b);
-    } else {
-      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&h);
-    }
-  }
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
 
 __device__ __forceinline__ float2 unpack2(uint32_t w, int bf16) {
   if (bf16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
