@@ -271,3 +271,34 @@ def test_decode_chunk_plan_matches_reference_loop():
     for F, n, ov in [(25, 14, 3), (25, 25, 3), (8, 4, 1), (14, 14, 3), (30, 14, 3), (5, 2, 3)]:
         assert _decode_chunks(F, n, ov) == reference_walk(F, n, ov), (F, n, ov)
     assert _decode_chunks(25, 14, 3) == [(0, 14, 0, 0), (11, 14, 11, 3)]
+
+
+def test_sampler_sees_through_the_reference_closure():
+    """sample_utils.do_sample wraps the engine in a local closure (sample_utils.py:314-315); our sampler recovers the
+    (Denoiser, B200Wrapper) pair from it so that the unmodified caller reaches the fused loop; foreign closures pass."""
+    from vista_b200 import spec
+    from vista_b200.diffusion import B200Denoiser, Denoiser, _unwrap_reference_closure
+    from vista_b200.modules import B200Wrapper, VideoUNet
+    cfg = spec.unet_preset("tiny")
+    unet = VideoUNet(in_channels=cfg.in_channels, model_channels=cfg.model_channels, out_channels=cfg.out_channels,
+                     num_res_blocks=cfg.num_res_blocks, attention_resolutions=list(cfg.attention_resolutions),
+                     channel_mult=list(cfg.channel_mult), num_head_channels=64, num_classes="sequential",
+                     context_dim=cfg.context_dim, adm_in_channels=cfg.adm_in_channels, extra_ff_mix_layer=True,
+                     use_spatial_context=True, merge_strategy="learned_with_images", video_kernel_size=[3, 1, 1],
+                     use_linear_in_transformer=True, action_control=True)
+
+    class Engine:                      # the attributes do_sample touches
+        pass
+    model = Engine()
+    model.model = B200Wrapper(unet)
+    model.denoiser = Denoiser({"target": "vista_b200.diffusion.VScalingWithEDMcNoise"}, num_frames=25)
+
+    def denoiser(x, sigma, cond, cond_mask):          # verbatim shape of the reference's closure
+        return model.denoiser(model.model, x, sigma, cond, cond_mask)
+
+    got = _unwrap_reference_closure(denoiser)
+    assert isinstance(got, B200Denoiser) and got.network is model.model and got.denoiser is model.denoiser
+    other = lambda x, sigma, cond, cond_mask: x
+    assert _unwrap_reference_closure(other) is other
+    k = 3
+    assert _unwrap_reference_closure(lambda x: x * k)(2) == 6

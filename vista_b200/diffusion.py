@@ -225,6 +225,26 @@ class B200Denoiser:
         return self.denoiser(self.network, x, sigma, c, cond_mask)
 
 
+def _unwrap_reference_closure(fn):
+    """The reference's callers hand the sampler a local closure, ``def denoiser(x, sigma, cond, cond_mask): return
+    model.denoiser(model.model, x, sigma, cond, cond_mask)`` (sample_utils.py:314-315, diffusion.py:324-325), which
+    hides the engine.  When that engine's network is a B200Wrapper and its denoiser is ours, recover the pair so that an
+    UNMODIFIED ``do_sample`` / ``DiffusionEngine.sample`` runs the fused loop; anything else is returned untouched."""
+    if isinstance(fn, B200Denoiser) or not callable(fn):
+        return fn
+    cells = getattr(fn, "__closure__", None) or ()
+    from .modules import B200Wrapper
+    for cell in cells:
+        try:
+            obj = cell.cell_contents
+        except ValueError:          # empty cell
+            continue
+        net, den = getattr(obj, "model", None), getattr(obj, "denoiser", None)
+        if isinstance(net, B200Wrapper) and isinstance(den, Denoiser):
+            return B200Denoiser(den, net)
+    return fn
+
+
 class BaseDiffusionSampler:
     def __init__(self, discretization_config, num_steps: Optional[int] = None, guider_config=None,
                  verbose: bool = False, device: str = "cuda"):
@@ -273,6 +293,7 @@ class EulerEDMSampler(BaseDiffusionSampler):
         return self.euler_step(x, d, dt)
 
     def __call__(self, denoiser, x, cond, uc=None, cond_frame=None, cond_mask=None, num_steps=None):
+        denoiser = _unwrap_reference_closure(denoiser)
         if isinstance(denoiser, B200Denoiser) and self.s_churn == 0.0 and self._fusable(denoiser, cond, uc):
             from .fused import fused_sample
             return fused_sample(self, denoiser, x, cond, uc, cond_frame, cond_mask, num_steps)
