@@ -23,13 +23,3 @@ run small        $F -k "small or upsample or timestep or layout or sampler"
 fi
 for extra in "$@"; do run "extra_$(basename $extra .py)" "$extra" -s; done
 cat gpurun_out/summary.txt
-# bring-up aid: if spatial attention failed, try the alternative V-descriptor stride assignments
-if [ -z "$SKIP_KERNELS" ] && ! grep -q "attn_sp rc=0" gpurun_out/summary.txt; then
-  for v in "1024 16384 2048" "1024 1024 2048" "16384 1024 1024"; do
-    set -- $v
-    VB_DBG_V_LBO=$1 VB_DBG_V_SBO=$2 VB_DBG_V_KSTEP=$3 timeout 300 python -m pytest -q --no-header -p no:cacheprovider \
-      tests/test_kernels_gpu.py -k "attention_spatial" > "gpurun_out/t_attn_sp_v_$1_$2_$3.log" 2>&1
-    echo "attn_sp variant lbo=$1 sbo=$2 kstep=$3 rc=$?" >> gpurun_out/summary.txt
-  done
-  cat gpurun_out/summary.txt
-fi

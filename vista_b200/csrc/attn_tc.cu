@@ -259,11 +259,8 @@ extern "C" int b200v_attention_spatial(const void* q, int64_t ld_q, const void* 
   p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   // MN-major SW128: 8-key groups 1024 B apart (SBO); a 16-key MMA step spans 2048 B; LBO (stride between
-  // 64-element groups along N) is unused for N = 64.  Env overrides exist for bring-up only.
+  // 64-element groups along N) is unused for N = 64.
   p.v_lbo = kTileBytes; p.v_sbo = 1024; p.v_kstep = 2048;
-  if (const char* e = getenv("VB_DBG_V_LBO")) p.v_lbo = atoi(e);
-  if (const char* e = getenv("VB_DBG_V_SBO")) p.v_sbo = atoi(e);
-  if (const char* e = getenv("VB_DBG_V_KSTEP")) p.v_kstep = atoi(e);
   const int smem_bytes = 1024 + 1024 + 9 * kTileBytes;
   static bool attr_set = false;
   if (!attr_set) {
