@@ -91,3 +91,63 @@ def test_cfg_split_topology_four_ranks():
         assert frames == [2 * half, 2 * half + 1]
         lo, hi = float(pair[0]), float(pair[1])
         assert both == [lo, lo, hi, hi]
+
+
+def _halo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vista_b200 import lib
+        from vista_b200.sharded import HaloExchange
+        nb, T, hw, C = 2, 3, 2, 4
+        a = torch.zeros(nb, T, hw, C)
+        send_first, send_last = torch.zeros(nb * hw, C), torch.zeros(nb * hw, C)
+        recv_prev, recv_next = torch.full((nb * hw, C), -1.0), torch.full((nb * hw, C), -1.0)
+        prev, nxt = par.halo_neighbours(rank, world)
+        halo = HaloExchange(None, prev, nxt,
+                            first=(send_first.view(nb, hw, C), a[:, 0], send_first, recv_prev),
+                            last=(send_last.view(nb, hw, C), a[:, T - 1], send_last, recv_next))
+
+        def fill(step):                       # frame t of rank r holds 100 r + 10 t + step
+            for t in range(T):
+                a[:, t] = 100.0 * rank + 10.0 * t + step
+        ok = []
+
+        def check(step):
+            if prev is not None:              # the previous rank's LAST frame
+                ok.append(bool((recv_prev == 100.0 * prev + 10.0 * (T - 1) + step).all()))
+            if nxt is not None:               # the next rank's FIRST frame
+                ok.append(bool((recv_next == 100.0 * nxt + step).all()))
+        fill(0)
+        lib.begin_tape()
+        lib.tape_host(halo.start)
+        lib.tape_host(halo.wait)
+        tape = lib.end_tape()
+        check(0)
+        for step in (1, 2, 3):                # replays pick up the new data through the same closures
+            fill(step)
+            lib.replay(tape)
+            check(step)
+        q.put((rank, ok, len(tape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_record_and_replay_four_ranks():
+    """sharded.HaloExchange under the launch tape, 4 ranks (two interior ranks with both neighbours): the recorded
+    start / wait closures move the right boundary frames on every replay."""
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, n in res:
+        assert n == 2
+        expect = 4 * ((rank > 0) + (rank < world - 1))
+        assert len(ok) == expect and all(ok), (rank, ok)

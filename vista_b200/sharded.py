@@ -35,6 +35,36 @@ from .spec import UNetConfig
 from .unet import Lin, UNetRuntime
 
 
+class HaloExchange:
+    """One-frame halo exchange of a (3,1,1) convolution between frame-shard neighbours: the first local frame goes to
+    the previous rank, the last one to the next rank, their boundary frames come back.  `start` / `wait` are plain
+    host callables so that they can sit on the launch tape (vista_b200.lib) between the kernels and be replayed;
+    `first` / `last` = (staging view, source view, send buffer, receive buffer).  Peers are GLOBAL ranks."""
+
+    def __init__(self, group, prev: Optional[int], nxt: Optional[int], first, last):
+        self.copies, self.p2p, self.pending = [], [], []
+        if prev is not None:
+            stage, src, send, recv = first
+            self.copies.append((stage, src))
+            self.p2p.append(dist.P2POp(dist.isend, send, prev, group))
+            self.p2p.append(dist.P2POp(dist.irecv, recv, prev, group))
+        if nxt is not None:
+            stage, src, send, recv = last
+            self.copies.append((stage, src))
+            self.p2p.append(dist.P2POp(dist.isend, send, nxt, group))
+            self.p2p.append(dist.P2POp(dist.irecv, recv, nxt, group))
+
+    def start(self):
+        for dst, src in self.copies:
+            dst.copy_(src)
+        self.pending = list(dist.batch_isend_irecv(self.p2p)) if self.p2p else []
+
+    def wait(self):
+        for r in self.pending:
+            r.wait()
+        self.pending = []
+
+
 class ShardedUNetRuntime(UNetRuntime):
     def __init__(self, cfg: UNetConfig, sd: Dict[str, torch.Tensor], device, num_frames: int = 25, group=None):
         self.group = group
@@ -109,26 +139,10 @@ class ShardedUNetRuntime(UNetRuntime):
         recv_next = self.buf("halo.rn", nb * hw, Cc)
         a4 = a.reshape(nb, T, hw, Cc) if a.is_contiguous() else None
         av = a4 if a4 is not None else a.as_strided((nb, T, hw, Cc), (T * hw * a.stride(0), hw * a.stride(0), a.stride(0), 1))
-        p2p, copies = [], []
-        if self.prev is not None:
-            copies.append((send_first.view(nb, hw, Cc), av[:, 0]))
-            p2p.append(dist.P2POp(dist.isend, send_first, self.prev, self.group))
-            p2p.append(dist.P2POp(dist.irecv, recv_prev, self.prev, self.group))
-        if self.next is not None:
-            copies.append((send_last.view(nb, hw, Cc), av[:, T - 1]))
-            p2p.append(dist.P2POp(dist.isend, send_last, self.next, self.group))
-            p2p.append(dist.P2POp(dist.irecv, recv_next, self.next, self.group))
-        pending = []
-
-        def start_halo():                  # host-side step, replayable (vista_b200.lib launch tape)
-            for dst, src in copies:
-                dst.copy_(src)
-            pending[:] = dist.batch_isend_irecv(p2p) if p2p else []
-
-        def wait_halo():
-            for r in pending:
-                r.wait()
-            pending.clear()
+        halo = HaloExchange(self.group, self.prev, self.next,
+                            first=(send_first.view(nb, hw, Cc), av[:, 0], send_first, recv_prev),
+                            last=(send_last.view(nb, hw, Cc), av[:, T - 1], send_last, recv_next))
+        start_halo, wait_halo = halo.start, halo.wait
         _lib.tape_host(start_halo)
         self.comm_bytes += 2 * nb * hw * Cc * 2 * ((self.prev is not None) + (self.next is not None))
         self.gemm(a, lin, out, taps=ops.TAPS_T3, geom=(hw, T, nb), **epi)
