@@ -195,6 +195,12 @@ int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, ld_net] fp32
                          int64_t ld_net, const float* cond_frame, const float* mask, const float* scales /* [T] */, const float* sigmas, int32_t* step_idx,
                          int32_t num_steps, int32_t T, int32_t h, int32_t w, void* stream);
 
+/* Diagnostic (not on the product path): SM cycles one tcgen05.mma kind::f16 K=16 (shared-memory operands, M in
+ * {64,128}, N) occupies the tensor pipe, from a train of 4*iters MMAs cycling over n_acc accumulators; one value per
+ * CTA in cycles_per_mma[n_ctas].  Drives the tile policy (profiles/r01_umma_n_sweep.md); tools/mma_probe.py. */
+int b200v_debug_mma_probe(int32_t M, int32_t N, int32_t iters, int32_t n_acc, int32_t a_mn_major, float* cycles_per_mma,
+                          int32_t n_ctas, void* stream);
+
 /* VAE decoder helpers.
  *   softmax_rows : fp32 scores -> fp16 probabilities, one row per block (mid.attn_1 single-head d=512
  *                  attention, vwm/modules/diffusionmodules/model.py:158-170, done as GEMM-softmax-GEMM)

@@ -1,0 +1,24 @@
+"""SM cycles per tcgen05.mma (kind::f16, K=16) by shape and accumulator count (b200v_debug_mma_probe).
+Usage: python tools/mma_probe.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from vista_b200 import lib
+l = lib.load()
+dev = torch.device("cuda:0")
+n_ctas = torch.cuda.get_device_properties(dev).multi_processor_count
+out = torch.zeros(n_ctas, dtype=torch.float32, device=dev)
+stream = torch.cuda.current_stream().cuda_stream
+print(f"{n_ctas} CTAs (one per SM), 2000 x 4 MMAs each; cycles per MMA (median over CTAs)")
+print("| M | N | accumulators | A major | cycles / MMA | nominal (M*N*16*2 / 8192) |")
+print("|---|---|---|---|---|---|")
+for M in (128, 64):
+    for N in (64, 128, 192, 256):
+        for n_acc in (1, 2):
+            if n_acc * N > 512:
+                continue
+            for a_mn in (0, 1):
+                lib.check(l.b200v_debug_mma_probe(M, N, 2000, n_acc, a_mn, out.data_ptr(), n_ctas, stream), "mma_probe")
+                torch.cuda.synchronize()
+                print(f"| {M} | {N} | {n_acc} | {'MN' if a_mn else 'K'} | {out.median().item():.1f} | {M * N * 32 / 8192:.0f} |", flush=True)

@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvista_b200.so")
-SOURCES = ["host.cu", "gemm_tc.cu", "attn_tc.cu", "attn2_tc.cu", "misc.cu"]
+SOURCES = ["host.cu", "gemm_tc.cu", "attn_tc.cu", "attn2_tc.cu", "misc.cu", "mma_probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -111,6 +111,7 @@ SIGNATURES = {
     "b200v_upsample2x": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_timestep_embedding": [_P, _I32, _I32, _F, _P, _I64, _P],
     "b200v_blend_emb": [_P, _P, _P, _P, _P, _P, _I32, _I32, _P],
+    "b200v_debug_mma_probe": [_I32, _I32, _I32, _I32, _I32, _P, _I32, _P],
     "b200v_sampler_prepare": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I32, _I32, _I32, _P],
     "b200v_sampler_update": [_P, _P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "b200v_softmax_rows": [_P, _I64, _P, _I64, _I64, _I32, _P],
