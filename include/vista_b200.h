@@ -97,6 +97,12 @@ int b200v_attention_spatial_v2(const void* q, int64_t ld_q, const void* k, int64
 int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                                void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
+/* EXPERIMENTAL (opt-in, VISTA_B200_ATTN=4; not validated on hardware at the time of writing): the v3 kernel with P kept in
+ * tensor memory (tcgen05.st into the consumed S columns, O += P V issued with the A operand in TMEM) instead of a
+ * shared-memory round trip. */
+int b200v_attention_spatial_v4(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                               void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
+
 /* Temporal self-attention over the T frames of each pixel (seq len T <= 32, head dim 64).
  * Replaces the batchified xformers call at vwm/modules/attention.py:384-399 reached from
  * vwm/modules/video_attention.py:127 and both "(b t) s c <-> (b s) t c" rearranges (:116,:140):

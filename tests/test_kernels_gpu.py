@@ -4,11 +4,16 @@ order; stated per test."""
 import math
 
 import numpy as np
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+
+# spatial-attention kernel generations under test; 4 (P in tensor memory) is experimental and opt-in
+ATTN_IMPLS = [1, 2, 3] + ([4] if os.environ.get("VISTA_B200_TEST_ATTN4") == "1" else [])
 
 
 @pytest.fixture(scope="module")
@@ -141,7 +146,7 @@ def test_gemm_temporal_conv(ops, nb, T, S, Cc):
 
 
 # ------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", ATTN_IMPLS)
 @pytest.mark.parametrize("frames,seq,heads", [(2, 128, 1), (3, 144, 2), (2, 576, 4), (1, 2304, 2), (2, 200, 1), (1, 256, 1),
                                               (2, 300, 1)])
 def test_attention_spatial(ops, frames, seq, heads, impl):
@@ -155,7 +160,7 @@ def test_attention_spatial(ops, frames, seq, heads, impl):
     check(out, ref, rtol=4e-3, atol=2e-3, name="attn spatial")
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", ATTN_IMPLS)
 def test_attention_spatial_peaky(ops, impl):
     """Large logits: the running max / (lazy) rescale path must hold (scores ~ +-40)."""
     frames, seq, heads = 1, 640, 1
@@ -168,7 +173,7 @@ def test_attention_spatial_peaky(ops, impl):
     check(out, ref, rtol=1e-2, atol=1e-2, name="attn peaky")
 
 
-@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("impl", [i for i in ATTN_IMPLS if i >= 2])
 def test_attention_spatial_increasing_max(ops, impl):
     """Keys ordered so that the row maximum keeps growing block after block: exercises every lazy-rescale branch."""
     seq = 1024

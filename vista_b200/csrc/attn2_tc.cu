@@ -350,7 +350,12 @@ namespace vb {
 #define VB_ATTN3_POLY_OF_8 0   // of every 8 exponentials, this many use exp2_poly (FMA pipe) instead of MUFU
 #endif
 
-template <int POLY8>
+// TS = true (b200v_attention_spatial_v4, opt-in): P does not go through shared memory.  The softmax threads write it as
+// packed fp16 into the TMEM columns of their own (already consumed) half of S with tcgen05.st, and O += P V is issued
+// with the A operand in TMEM.  The single-thread issue order keeps S(j+1) behind the PV(j) that reads the aliased
+// columns.  Motivation: with shared-memory operands every MMA costs ~90 ns however small N is (profiles/
+// r01_umma_n_sweep.md); the 8 PV MMAs (N = 80) are two thirds of the kernel's tensor time.
+template <int POLY8, bool TS>
 __global__ void __launch_bounds__(384, 2)
 attn3_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
@@ -445,9 +450,15 @@ attn3_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t ad = make_desc_sw128(p_base + (k >> 2) * kT2Bytes + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_desc_sw128(v_base + k * 2048, lbo, 1024);
-          umma_f16(tmem_base + 128, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+          if (TS) {
+            // keys 16 k .. 16 k + 15 of half k / 4: 8 packed columns inside that half's S range
+            const uint64_t bd = make_desc_sw128(v_base + k * 2048, lbo, 1024);
+            umma_f16_ts(tmem_base + 128, tmem_base + (k >> 2) * 64 + (k & 3) * 8, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t ad = make_desc_sw128(p_base + (k >> 2) * kT2Bytes + (k & 3) * 32, 16, 1024);
+            const uint64_t bd = make_desc_sw128(v_base + k * 2048, lbo, 1024);
+            umma_f16(tmem_base + 128, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(v_empty);
         umma_commit(o_full);
@@ -523,6 +534,7 @@ attn3_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= kv_left) s[i] = 0xFF800000u;
         }
+        uint32_t pw[16];                   // TS: the 32 keys of this chunk as 16 packed fp16 pairs
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {   // 8 keys = one 16-byte chunk
           uint32_t w[4];
@@ -534,14 +546,20 @@ attn3_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const float p0 = ((e0 & 7) < POLY8) ? exp2_poly(x0) : ex2_f(x0);
             const float p1 = ((e1 & 7) < POLY8) ? exp2_poly(x1) : ex2_f(x1);
             w[i] = pack_h2(p0, p1);
+            pw[q4 * 4 + i] = w[i];
           }
-          const int chunk = c * 4 + q4;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((chunk ^ sw) << 4)), "r"(w[0]), "r"(w[1]),
-                       "r"(w[2]), "r"(w[3])
-                       : "memory");
+          if (!TS) {
+            const int chunk = c * 4 + q4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((chunk ^ sw) << 4)), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
         }
+        // keys [32 c, 32 c + 32) of this half -> packed columns [16 c, 16 c + 16) of the half's own S range: those S
+        // columns were consumed in this or the previous chunk iteration
+        if (TS) tmem_st16(tS + c * 16, pw);
       }
-      fence_proxy_async_smem();
+      if (TS) tmem_st_wait(); else fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
@@ -576,9 +594,8 @@ attn3_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 }  // namespace vb
 
-extern "C" int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
-                                          int64_t ld_v, void* out, int64_t ld_o, int32_t frames, int32_t seq,
-                                          int32_t heads, void* stream_) {
+static int attn3_launch(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, void* out,
+                        int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream_, bool ts) {
   using namespace vb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VB_REQUIRE(q && k && v && out, "b200v_attention_spatial_v3: null pointer");
@@ -607,16 +624,35 @@ extern "C" int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const voi
   if (poly < 0) {
     poly = VB_ATTN3_POLY_OF_8;
     if (const char* e = getenv("VB_ATTN3_POLY")) poly = atoi(e);   // tuning knob: exponentials (of 8) on the FMA pipe
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
   dim3 grid((seq + kT2 - 1) / kT2, heads, frames);
-  if (poly <= 0) attn3_spatial_kernel<0><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
-  else if (poly <= 2) attn3_spatial_kernel<2><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
-  else if (poly == 3) attn3_spatial_kernel<3><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
-  else attn3_spatial_kernel<4><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  if (ts) {
+    static bool ts_attr = false;
+    if (!ts_attr) {
+      VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      ts_attr = true;
+    }
+    attn3_spatial_kernel<0, true><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  } else if (poly <= 0) attn3_spatial_kernel<0, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  else if (poly <= 2) attn3_spatial_kernel<2, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  else if (poly == 3) attn3_spatial_kernel<3, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  else attn3_spatial_kernel<4, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
+                                          int64_t ld_v, void* out, int64_t ld_o, int32_t frames, int32_t seq,
+                                          int32_t heads, void* stream) {
+  return attn3_launch(q, ld_q, k, ld_k, v, ld_v, out, ld_o, frames, seq, heads, stream, false);
+}
+
+extern "C" int b200v_attention_spatial_v4(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
+                                          int64_t ld_v, void* out, int64_t ld_o, int32_t frames, int32_t seq,
+                                          int32_t heads, void* stream) {
+  return attn3_launch(q, ld_q, k, ld_k, v, ld_v, out, ld_o, frames, seq, heads, stream, true);
 }

@@ -96,6 +96,7 @@ SIGNATURES = {
     "b200v_attention_spatial": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v2": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v3": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
+    "b200v_attention_spatial_v4": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_groupnorm_chunk": [],
     "b200v_groupnorm_chunk_for": [C.c_int32, C.c_int32],

@@ -177,7 +177,8 @@ ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "3"))   # 3: two CTAs/SM, two 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
     l = _lib.load()
-    fn = {1: l.b200v_attention_spatial, 2: l.b200v_attention_spatial_v2, 3: l.b200v_attention_spatial_v3}[impl or ATTN_IMPL]
+    fn = {1: l.b200v_attention_spatial, 2: l.b200v_attention_spatial_v2, 3: l.b200v_attention_spatial_v3,
+          4: l.b200v_attention_spatial_v4}[impl or ATTN_IMPL]     # 4: experimental P-in-TMEM variant (opt-in)
     _count(1)
     _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
                 2.0 * 4 * frames * seq * heads * 64)
