@@ -204,8 +204,9 @@ int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, ld_net] fp32
 /* Diagnostic (not on the product path): SM cycles one tcgen05.mma kind::f16 K=16 (shared-memory operands, M in
  * {64,128}, N) occupies the tensor pipe, from a train of 4*iters MMAs cycling over n_acc accumulators; one value per
  * CTA in cycles_per_mma[n_ctas].  Drives the tile policy (profiles/r01_umma_n_sweep.md); tools/mma_probe.py. */
-int b200v_debug_mma_probe(int32_t M, int32_t N, int32_t iters, int32_t n_acc, int32_t a_mn_major, float* cycles_per_mma,
-                          int32_t n_ctas, void* stream);
+int b200v_debug_mma_probe(int32_t M, int32_t N, int32_t iters, int32_t n_acc, int32_t a_mn_major,
+                          int32_t a_in_tmem /* A operand from tensor memory instead of shared memory */,
+                          float* cycles_per_mma, int32_t n_ctas, void* stream);
 
 /* VAE decoder helpers.
  *   softmax_rows : fp32 scores -> fp16 probabilities, one row per block (mid.attn_1 single-head d=512

@@ -11,14 +11,16 @@ n_ctas = torch.cuda.get_device_properties(dev).multi_processor_count
 out = torch.zeros(n_ctas, dtype=torch.float32, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
 print(f"{n_ctas} CTAs (one per SM), 2000 x 4 MMAs each; cycles per MMA (median over CTAs)")
-print("| M | N | accumulators | A major | cycles / MMA | nominal (M*N*16*2 / 8192) |")
+print("| M | N | accumulators | A operand | cycles / MMA | nominal (max(M,128)*N/256) |")
 print("|---|---|---|---|---|---|")
 for M in (128, 64):
-    for N in (64, 128, 192, 256):
+    for N in (64, 80, 128, 192, 256):
+        if N % (16 if M == 128 else 8):
+            continue
         for n_acc in (1, 2):
-            if n_acc * N > 512:
-                continue
-            for a_mn in (0, 1):
-                lib.check(l.b200v_debug_mma_probe(M, N, 2000, n_acc, a_mn, out.data_ptr(), n_ctas, stream), "mma_probe")
+            for mode, (a_mn, a_tm) in (("smem K-major", (0, 0)), ("smem MN-major", (1, 0)), ("TMEM", (0, 1))):
+                if n_acc * N > (480 if a_tm else 512):
+                    continue
+                lib.check(l.b200v_debug_mma_probe(M, N, 2000, n_acc, a_mn, a_tm, out.data_ptr(), n_ctas, stream), "mma_probe")
                 torch.cuda.synchronize()
-                print(f"| {M} | {N} | {n_acc} | {'MN' if a_mn else 'K'} | {out.median().item():.1f} | {M * N * 32 / 8192:.0f} |", flush=True)
+                print(f"| {M} | {N} | {n_acc} | {mode} | {out.median().item():.1f} | {max(M, 128) * N / 256:.0f} |", flush=True)

@@ -12,7 +12,7 @@
 namespace vb {
 
 __global__ void __launch_bounds__(128, 1)
-mma_probe_kernel(int M, int N, int iters, int n_acc, int a_mn_major, float* __restrict__ cycles_per_mma) {
+mma_probe_kernel(int M, int N, int iters, int n_acc, int a_mn_major, int a_in_tmem, float* __restrict__ cycles_per_mma) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -43,8 +43,12 @@ mma_probe_kernel(int M, int N, int iters, int n_acc, int a_mn_major, float* __re
     for (int it = 0; it < iters; ++it) {
       const uint32_t d = tmem_base + acc * N;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) {
+        if (a_in_tmem)     // A operand: 8 packed columns per K = 16 step, placed behind the accumulators
+          umma_f16_ts(d, tmem_base + 480 + 8 * k, desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+        else
+          umma_f16(d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+      }
       if (++acc == n_acc) acc = 0;
     }
     umma_commit(done);
@@ -63,19 +67,20 @@ mma_probe_kernel(int M, int N, int iters, int n_acc, int a_mn_major, float* __re
 }  // namespace vb
 
 extern "C" int b200v_debug_mma_probe(int32_t M, int32_t N, int32_t iters, int32_t n_acc, int32_t a_mn_major,
-                                     float* cycles_per_mma, int32_t n_ctas, void* stream) {
+                                     int32_t a_in_tmem, float* cycles_per_mma, int32_t n_ctas, void* stream) {
   using namespace vb;
   VB_REQUIRE(cycles_per_mma && n_ctas > 0, "mma_probe: null output");
   VB_REQUIRE(M == 64 || M == 128, "mma_probe: M=%d must be 64 or 128", M);
   VB_REQUIRE(N >= 8 && N <= 256 && N % (M == 128 ? 16 : 8) == 0, "mma_probe: N=%d invalid for M=%d", N, M);
-  VB_REQUIRE(iters > 0 && n_acc >= 1 && n_acc * N <= 512, "mma_probe: iters / n_acc out of range");
+  VB_REQUIRE(iters > 0 && n_acc >= 1 && n_acc * N <= (a_in_tmem ? 480 : 512), "mma_probe: iters / n_acc out of range");
   const int smem_bytes = 1024 + 1024 + (128 + 256) * 128;
   static bool attr_set = false;
   if (!attr_set) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
-  mma_probe_kernel<<<n_ctas, 128, smem_bytes, (cudaStream_t)stream>>>(M, N, iters, n_acc, a_mn_major, cycles_per_mma);
+  mma_probe_kernel<<<n_ctas, 128, smem_bytes, (cudaStream_t)stream>>>(M, N, iters, n_acc, a_mn_major, a_in_tmem,
+                                                                       cycles_per_mma);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -112,7 +112,7 @@ SIGNATURES = {
     "b200v_upsample2x": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_timestep_embedding": [_P, _I32, _I32, _F, _P, _I64, _P],
     "b200v_blend_emb": [_P, _P, _P, _P, _P, _P, _I32, _I32, _P],
-    "b200v_debug_mma_probe": [_I32, _I32, _I32, _I32, _I32, _P, _I32, _P],
+    "b200v_debug_mma_probe": [_I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P],
     "b200v_sampler_prepare": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I32, _I32, _I32, _P],
     "b200v_sampler_update": [_P, _P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "b200v_softmax_rows": [_P, _I64, _P, _I64, _I64, _I32, _P],
