@@ -54,7 +54,8 @@ for (M, C, geom) in ((460800, 320, (128, 72, 50)), (115200, 640, (64, 36, 50))):
     heads, seq = C // 64, geom[0] * geom[1]
     o = torch.empty(M, C, dtype=torch.float16, device=dev)
     qkv = torch.randn(M, 3 * C, device=dev).half()
-    for impl in ((3,) if only else (1, 2, 3)):
+    impls = tuple(int(v) for v in os.environ["BENCH_ATTN_IMPLS"].split(",")) if os.environ.get("BENCH_ATTN_IMPLS") else ((3,) if only else (1, 2, 3))
+    for impl in impls:
         timeit(f"attention spatial v{impl} seq={seq} heads={heads}",
                lambda: ops.attention_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, 50, seq, heads, impl=impl),
                4.0 * 64 * heads * 50 * seq * seq, 2.0 * 4 * M * C, reps=3)
