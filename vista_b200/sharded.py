@@ -178,8 +178,9 @@ class ShardedUNetRuntime(UNetRuntime):
         T, Tp, W = self.T, self.T_pad, self.world
         send = self.buf("kv.send", nb * Tp * hw, 2 * Cc)
         recv = self.buf("kv.recv", W * nb * Tp * hw, 2 * Cc)
-        kv = qkv[:, Cc:].reshape(nb, T, hw, 2 * Cc) if False else qkv.as_strided(
-            (nb, T, hw, 2 * Cc), (T * hw * qkv.stride(0), hw * qkv.stride(0), qkv.stride(0), 1), qkv.storage_offset() + Cc)
+        # the K|V column block of the fused q|k|v projection as a strided (clip, frame, pixel, 2C) view
+        kv = qkv.as_strided((nb, T, hw, 2 * Cc), (T * hw * qkv.stride(0), hw * qkv.stride(0), qkv.stride(0), 1),
+                            qkv.storage_offset() + Cc)
         dst = send.view(nb, Tp, hw, 2 * Cc)[:, :T]
         _lib.tape_host(lambda: dst.copy_(kv))
         _lib.tape_host(lambda: dist.all_gather_into_tensor(recv, send, group=self.group))
