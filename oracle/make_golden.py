@@ -138,6 +138,57 @@ def gen_decode_fs(name):
                         weight_checksum=synth.state_dict_checksum(sd))
 
 
+# name -> (encoder preset, image h, image w, frames)
+ENCODER_CASES = {
+    "encoder_tiny": ("tiny", 32, 64, 5),
+    "encoder_small": ("small", 64, 128, 3),
+}
+
+
+def gen_encoder(name):
+    """Reference Encoder moments, and DiffusionEngine.encode_first_stage (models/diffusion.py:183-195, called unbound on
+    a stand-in engine) through AutoencodingEngine.encode's regulariser (DiagonalGaussianRegularizer, sample=True) with
+    the device RNG replaced by a recorded noise tensor."""
+    preset, h, w, n = ENCODER_CASES[name]
+    cfg = spec.encoder_preset(preset)
+    sd = synth.synth_state_dict(spec.encoder_param_specs(cfg), seed=3)
+    enc = ref_loader.build_ref_encoder(cfg)
+    enc.load_state_dict(to_t(sd), strict=True)
+    x = synth.normal(11, "enc.x", (n, cfg.in_channels, h, w), std=0.5)
+    with torch.no_grad():
+        mom = enc(torch.from_numpy(x))
+    from vwm.models.diffusion import DiffusionEngine
+    from vwm.modules.autoencoding.regularizers import DiagonalGaussianRegularizer
+    reg = DiagonalGaussianRegularizer()
+    noise = synth.normal(12, "enc.noise", (n, cfg.z_channels, mom.shape[2], mom.shape[3]), std=1.0)
+    calls = {"i": 0}
+    n_chunk = 2
+    real_randn = torch.randn
+
+    def fake_randn(*shape, **kw):              # the regulariser draws mean.shape per chunk, in order
+        shp = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+        i = calls["i"]
+        calls["i"] += shp[0]
+        out = torch.from_numpy(noise[i:i + shp[0]])
+        assert tuple(out.shape) == shp, (out.shape, shp)
+        return out
+    fsm = types.SimpleNamespace(encode=lambda xx: reg(enc(xx))[0])
+    eng = types.SimpleNamespace(scale_factor=0.18215, en_and_decode_n_samples_a_time=n_chunk,
+                                disable_first_stage_autocast=True, first_stage_model=fsm)
+    fn = DiffusionEngine.encode_first_stage
+    fn = getattr(fn, "__wrapped__", fn)
+    torch.randn = fake_randn
+    try:
+        with torch.no_grad():
+            z = fn(eng, torch.from_numpy(x))
+    finally:
+        torch.randn = real_randn
+    assert calls["i"] == n
+    print(f"{name}: moments {tuple(mom.shape)} absmean {mom.abs().mean():.4f}; z absmean {z.abs().mean():.4f}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), moments=mom.numpy(), z=z.numpy(), n_chunk=n_chunk,
+                        weight_checksum=synth.state_dict_checksum(sd))
+
+
 def gen_anchors():
     """Closed-form pieces straight from the reference classes."""
     ref = ref_loader.load_reference()
@@ -186,7 +237,7 @@ def gen_full_step():
 
 def main(argv):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    cases = argv or (["anchors"] + list(UNET_CASES) + list(SAMPLER_CASES) + list(DECODER_CASES) + list(DECODE_FS_CASES))
+    cases = argv or (["anchors"] + list(UNET_CASES) + list(SAMPLER_CASES) + list(DECODER_CASES) + list(DECODE_FS_CASES) + list(ENCODER_CASES))
     for cname in cases:
         if cname == "anchors":
             gen_anchors()
@@ -198,6 +249,8 @@ def main(argv):
             gen_decoder(cname)
         elif cname in DECODE_FS_CASES:
             gen_decode_fs(cname)
+        elif cname in ENCODER_CASES:
+            gen_encoder(cname)
         elif cname == "vista_full_step":
             gen_full_step()
         else:

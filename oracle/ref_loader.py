@@ -117,6 +117,18 @@ def build_ref_decoder(cfg):
         return ref.VideoDecoder(**params).eval()
 
 
+def build_ref_encoder(cfg):
+    """Reference ``Encoder`` (vwm/modules/diffusionmodules/model.py:445) for a ``vista_b200.spec.EncoderConfig``; other
+    ctor args as in configs/inference/vista.yaml:155-168."""
+    load_reference()
+    from vwm.modules.diffusionmodules.model import Encoder
+    params = dict(vista_yaml()["model"]["params"]["first_stage_config"]["params"]["encoder_config"]["params"])
+    params.update(ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, z_channels=cfg.z_channels,
+                  in_channels=cfg.in_channels, double_z=cfg.double_z)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return Encoder(**params).eval()
+
+
 def build_ref_sampler(num_steps, guider="VanillaCFG", scale=2.5, num_frames=25):
     ref = load_reference()
     if guider == "VanillaCFG":

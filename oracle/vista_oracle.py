@@ -377,3 +377,52 @@ def decode_first_stage(sd: SD, cfg: DecoderConfig, z: torch.Tensor, scale_factor
         for cur in z.split(n_samples, dim=0):
             outs.append(decoder_forward(sd, cfg, cur, timesteps=cur.shape[0]))
     return torch.cat(outs, dim=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# VAE encoder (the next row; oracle first)
+# ---------------------------------------------------------------------------------------------
+def enc_res_block(sd: SD, p: str, x: torch.Tensor, has_skip: bool) -> torch.Tensor:
+    """model.py:116-135 with temb = None (Encoder sets temb_ch = 0, model.py:467)."""
+    h = F.conv2d(_swish(_gn(sd, f"{p}.norm1", x, 1e-6)), sd[f"{p}.conv1.weight"], sd[f"{p}.conv1.bias"], padding=1)
+    h = F.conv2d(_swish(_gn(sd, f"{p}.norm2", h, 1e-6)), sd[f"{p}.conv2.weight"], sd[f"{p}.conv2.bias"], padding=1)
+    if has_skip:
+        x = F.conv2d(x, sd[f"{p}.nin_shortcut.weight"], sd[f"{p}.nin_shortcut.bias"])
+    return x + h
+
+
+def encoder_forward(sd: SD, cfg, x: torch.Tensor) -> torch.Tensor:
+    """Encoder.forward (model.py:527-557): conv_in, per level ResnetBlocks (+ Downsample: zero pad right / bottom by
+    one, conv3x3 stride 2 without padding, model.py:69-83), mid (res, attn, res), GN, swish, conv_out ->
+    (n, 2 z_channels, h/8, w/8) moments."""
+    from vista_b200.spec import build_encoder_plan
+    levels, mid_ch = build_encoder_plan(cfg)
+    h = F.conv2d(x, sd["conv_in.weight"], sd["conv_in.bias"], padding=1)
+    for blocks, down, _ in levels:
+        for rb in blocks:
+            h = enc_res_block(sd, rb.prefix, h, rb.has_skip)
+        if down is not None:
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[f"{down}.weight"], sd[f"{down}.bias"], stride=2)
+    h = enc_res_block(sd, "mid.block_1", h, False)
+    h = dec_attn_block(sd, "mid.attn_1", h)
+    h = enc_res_block(sd, "mid.block_2", h, False)
+    h = _swish(_gn(sd, "norm_out", h, 1e-6))
+    return F.conv2d(h, sd["conv_out.weight"], sd["conv_out.bias"], padding=1)
+
+
+def encode_first_stage(sd: SD, cfg, x: torch.Tensor, scale_factor=0.18215, n_samples: Optional[int] = None,
+                       noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DiffusionEngine.encode_first_stage (models/diffusion.py:183-195) over AutoencodingEngine.encode
+    (autoencoder.py:190-203) with DiagonalGaussianRegularizer (regularizers/__init__.py:30-40): chunks of n_samples
+    frames, z = mean + exp(0.5 clamp(logvar, -30, 20)) * noise (distributions.py:25-36; the reference draws the noise
+    on the device: inject it), noise = None gives the mode; times scale_factor."""
+    n_samples = x.shape[0] if n_samples is None else n_samples
+    outs = []
+    for i in range(0, x.shape[0], n_samples):
+        mom = encoder_forward(sd, cfg, x[i:i + n_samples])
+        mean, logvar = torch.chunk(mom, 2, dim=1)
+        z = mean
+        if noise is not None:
+            z = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise[i:i + n_samples]
+        outs.append(z)
+    return torch.cat(outs, dim=0) * scale_factor

@@ -97,3 +97,33 @@ def test_decode_first_stage_matches_reference():
     ref = torch.from_numpy(g["out"])
     assert out.shape == ref.shape == (25, 3, 16, 32)
     assert rel_l2(out, ref) < 2e-5, rel_l2(out, ref)
+
+
+# ---- VAE encoder: SURVEY.md §8f rank 1 (the next row) — oracle pinned before any kernel work ----
+@pytest.mark.parametrize("name,preset,h,w,n", [("encoder_tiny", "tiny", 32, 64, 5), ("encoder_small", "small", 64, 128, 3)])
+def test_encoder_matches_reference(name, preset, h, w, n):
+    if not has_golden(name):
+        pytest.skip("fixture not generated")
+    g = golden(name)
+    cfg = spec.encoder_preset(preset)
+    sd = synth.synth_state_dict(spec.encoder_param_specs(cfg), seed=3)
+    assert synth.state_dict_checksum(sd) == str(g["weight_checksum"])
+    x = torch.from_numpy(synth.normal(11, "enc.x", (n, cfg.in_channels, h, w), std=0.5))
+    with torch.no_grad():
+        mom = vo.encoder_forward(to_t(sd), cfg, x)
+    ref = torch.from_numpy(g["moments"])
+    assert mom.shape == ref.shape == (n, 2 * cfg.z_channels, h // 2 ** (len(cfg.ch_mult) - 1), w // 2 ** (len(cfg.ch_mult) - 1))
+    assert rel_l2(mom, ref) < 2e-5, rel_l2(mom, ref)
+    # encode_first_stage: chunked, sampled with the recorded noise (the reference draws it from the device RNG), scaled
+    noise = torch.from_numpy(synth.normal(12, "enc.noise", (n, cfg.z_channels, mom.shape[2], mom.shape[3]), std=1.0))
+    with torch.no_grad():
+        z = vo.encode_first_stage(to_t(sd), cfg, x, n_samples=int(g["n_chunk"]), noise=noise)
+        z_mode = vo.encode_first_stage(to_t(sd), cfg, x)
+    assert rel_l2(z, torch.from_numpy(g["z"])) < 2e-5
+    assert torch.allclose(z_mode, ref[:, :cfg.z_channels] * 0.18215, rtol=1e-4, atol=1e-6)
+
+
+def test_encoder_param_inventory():
+    # 34.2 M parameters
+    e = spec.encoder_param_specs(spec.encoder_preset("vista"))
+    assert len(e) == 106 and sum(int(np.prod(v[0])) for v in e.values()) == 34163592

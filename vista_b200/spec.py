@@ -58,8 +58,21 @@ class DecoderConfig:
     num_groups: int = 32
 
 
+@dataclass
+class EncoderConfig:
+    """``Encoder`` arguments (configs/inference/vista.yaml:155-168); SURVEY.md §8f rank 1 (next row)."""
+    ch: int = 128
+    in_channels: int = 3
+    ch_mult: Sequence[int] = (1, 2, 4, 4)
+    num_res_blocks: int = 2
+    z_channels: int = 4
+    double_z: bool = True
+    num_groups: int = 32
+
+
 VISTA_UNET = UNetConfig()
 VISTA_DECODER = DecoderConfig()
+VISTA_ENCODER = EncoderConfig()
 
 
 # --------------------------------------------------------------------------------------
@@ -356,6 +369,56 @@ def decoder_param_specs(cfg: DecoderConfig = VISTA_DECODER) -> Dict[str, ParamSp
     return out
 
 
+# ---- VAE encoder (2-D, per frame) ----------------------------------------------------
+def build_encoder_plan(cfg: EncoderConfig = VISTA_ENCODER):
+    """model.py:476-523: per level the ResnetBlocks (prefix, cin, cout) and the Downsample conv prefix (or None);
+    then the mid channel count."""
+    levels = []
+    in_ch_mult = (1,) + tuple(cfg.ch_mult)
+    block_in = cfg.ch
+    for i_level in range(len(cfg.ch_mult)):
+        block_in = cfg.ch * in_ch_mult[i_level]
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        blocks = []
+        for i_block in range(cfg.num_res_blocks):
+            blocks.append(DecResBlockSpec(f"down.{i_level}.block.{i_block}", block_in, block_out))
+            block_in = block_out
+        down = f"down.{i_level}.downsample.conv" if i_level != len(cfg.ch_mult) - 1 else None
+        levels.append((blocks, down, block_in))
+    return levels, block_in
+
+
+def _enc_resblock_params(out, rb: DecResBlockSpec):
+    p = rb.prefix
+    _norm(out, f"{p}.norm1", rb.cin)
+    _conv(out, f"{p}.conv1", rb.cin, rb.cout, (3, 3))
+    _norm(out, f"{p}.norm2", rb.cout)
+    _conv(out, f"{p}.conv2", rb.cout, rb.cout, (3, 3))
+    if rb.has_skip:
+        _conv(out, f"{p}.nin_shortcut", rb.cin, rb.cout, (1, 1))
+
+
+def encoder_param_specs(cfg: EncoderConfig = VISTA_ENCODER) -> Dict[str, ParamSpec]:
+    """name -> (shape, kind) for ``Encoder.state_dict()`` (keys relative to the encoder)."""
+    levels, mid_ch = build_encoder_plan(cfg)
+    out: Dict[str, ParamSpec] = {}
+    _conv(out, "conv_in", cfg.in_channels, cfg.ch, (3, 3))
+    for blocks, down, ch in levels:
+        for rb in blocks:
+            _enc_resblock_params(out, rb)
+        if down is not None:
+            _conv(out, down, ch, ch, (3, 3))
+    _enc_resblock_params(out, DecResBlockSpec("mid.block_1", mid_ch, mid_ch))
+    a = "mid.attn_1"
+    _norm(out, f"{a}.norm", mid_ch)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(out, f"{a}.{n}", mid_ch, mid_ch, (1, 1))
+    _enc_resblock_params(out, DecResBlockSpec("mid.block_2", mid_ch, mid_ch))
+    _norm(out, "norm_out", mid_ch)
+    _conv(out, "conv_out", mid_ch, (2 if cfg.double_z else 1) * cfg.z_channels, (3, 3))
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # presets used by tests / oracle / bench
 # --------------------------------------------------------------------------------------
@@ -377,4 +440,14 @@ def decoder_preset(name: str) -> DecoderConfig:
         return DecoderConfig(ch=64)
     if name == "tiny":
         return DecoderConfig(ch=64, ch_mult=(1, 2), num_res_blocks=1)
+    raise KeyError(name)
+
+
+def encoder_preset(name: str) -> EncoderConfig:
+    if name == "vista":
+        return EncoderConfig()
+    if name == "small":
+        return EncoderConfig(ch=64)
+    if name == "tiny":
+        return EncoderConfig(ch=64, ch_mult=(1, 2), num_res_blocks=1)
     raise KeyError(name)
