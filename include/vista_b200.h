@@ -168,6 +168,9 @@ int b200v_conv3x3_small_cout(const void* x, int64_t ldx, int32_t cin, const floa
 /* Data movement: stride-2 im2col for Downsample (openaimodel.py:129-136), nearest 2x upsample
  * (openaimodel.py:100; model.py:63). */
 int b200v_im2col_s2(const void* x, int64_t ldx, void* out, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream);
+/* VAE-encoder Downsample (vwm/modules/diffusionmodules/model.py:69-83): pad right / bottom by one, stride 2, no other
+ * padding: out[(b,ho,wo), tap*C + c] = x[b, 2ho+kh, 2wo+kw, c], Ho = (H-2)/2 + 1.  (Next row: the VAE encoder.) */
+int b200v_im2col_s2_asym(const void* x, int64_t ldx, void* out, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream);
 int b200v_upsample2x(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t NB, int32_t H, int32_t W, int32_t C,
                      void* stream);
 

@@ -589,6 +589,28 @@ __global__ void im2col_s2_kernel(const __half* __restrict__ x, long long ldx, __
   }
 }
 
+// VAE-encoder Downsample (model.py:69-83): zero pad by one on the right / bottom only, conv3x3 stride 2 without
+// padding: out[(b, ho, wo), tap*C + c] = x[b, 2ho + kh, 2wo + kw, c] (zero beyond H, W), Ho = (H - 2) / 2 + 1.
+__global__ void im2col_s2_asym_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ out, int NB,
+                                      int H, int W, int C) {
+  const int Ho = (H - 2) / 2 + 1, Wo = (W - 2) / 2 + 1;
+  const int nvec = C >> 3;
+  const long long total = (long long)NB * Ho * Wo * 9 * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long r = i / nvec;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho);
+    const long long b = r / ((long long)Wo * Ho);
+    const int hh = 2 * ho + tap / 3, ww = 2 * wo + tap % 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (hh < H && ww < W)
+      val = __ldg(reinterpret_cast<const uint4*>(x + ((b * H + hh) * W + ww) * ldx + v * 8));
+    *reinterpret_cast<uint4*>(out + r * (9LL * C) + (long long)tap * C + v * 8) = val;
+  }
+}
+
 __global__ void upsample2x_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ out, long long ldo,
                                   int NB, int H, int W, int C) {
   const int nvec = C >> 3;
@@ -938,6 +960,17 @@ extern "C" int b200v_im2col_s2(const void* x, int64_t ldx, void* out, int32_t NB
   const long long total = (long long)NB * Ho * Wo * 9 * (C / 8);
   im2col_s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)out, NB, H,
                                                                            W, C);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200v_im2col_s2_asym(const void* x, int64_t ldx, void* out, int32_t NB, int32_t H, int32_t W, int32_t C,
+                                    void* stream) {
+  VB_REQUIRE(x && out && C % 8 == 0 && ldx % 8 == 0 && H >= 2 && W >= 2, "im2col_s2_asym: bad args");
+  const int Ho = (H - 2) / 2 + 1, Wo = (W - 2) / 2 + 1;
+  const long long total = (long long)NB * Ho * Wo * 9 * (C / 8);
+  im2col_s2_asym_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)out, NB,
+                                                                                H, W, C);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,7 +1,7 @@
 """``DiffusionEngine`` surface (vwm/models/diffusion.py:20-131,150-180,306-329) for the hot path: the attributes
 and methods ``sample_utils`` uses (.model, .denoiser, .first_stage_model, .scale_factor, .decode_first_stage,
-.sample, .ema_scope) on top of the B200 executors.  Training, the conditioner and the VAE encoder are out of
-scope: ``encode_first_stage`` / ``conditioner`` raise instead of silently doing something else."""
+.sample, .ema_scope) on top of the B200 executors.  Training and the conditioner are out of scope and raise; the VAE encoder is the next row
+(§8f): ``encode_first_stage`` works when an (experimental) ``encoder_config: vista_b200.vae.Encoder`` is given, else raises."""
 from __future__ import annotations
 
 import contextlib
@@ -19,15 +19,22 @@ class FirstStage(nn.Module):
     """Holds the decoder under the reference's key prefix ``first_stage_model.decoder.*``
     (AutoencodingEngine.decode, vwm/models/autoencoder.py:206-208)."""
 
-    def __init__(self, decoder_config: Dict, **ignored):
+    def __init__(self, decoder_config: Dict, encoder_config: Optional[Dict] = None, **ignored):
         super().__init__()
         self.decoder = instantiate_from_config(decoder_config)
+        # optional: the experimental B200 encoder (SURVEY.md §8f rank 1, vista_b200.vae.Encoder), keys
+        # ``first_stage_model.encoder.*`` as in the reference checkpoint
+        if encoder_config is not None:
+            self.encoder = instantiate_from_config(encoder_config)
 
     def decode(self, z: torch.Tensor, **kwargs) -> torch.Tensor:
         return self.decoder(z, **kwargs)
 
     def encode(self, x, **kwargs):
-        raise NotImplementedError("the VAE encoder runs once per sample and is outside the B200 hot path (SURVEY.md §8f)")
+        if not hasattr(self, "encoder"):
+            raise NotImplementedError("no encoder_config given: the VAE encoder is the next row after the hot path "
+                                      "(SURVEY.md §8f); pass latents, or add encoder_config: vista_b200.vae.Encoder")
+        return self.encoder(x)                 # moments (mean | logvar); sampling lives in encode_first_stage
 
 
 class DiffusionEngine(nn.Module):
@@ -44,7 +51,8 @@ class DiffusionEngine(nn.Module):
         self.sampler = instantiate_from_config(sampler_config) if sampler_config is not None else None
         if first_stage_config is not None:
             params = first_stage_config.get("params", first_stage_config)
-            self.first_stage_model = FirstStage(params["decoder_config"])
+            self.first_stage_model = FirstStage(params["decoder_config"], params.get("encoder_config")
+                                                if str(params.get("encoder_config", {}).get("target", "")).startswith("vista_b200.") else None)
         else:
             self.first_stage_model = None
         self.scale_factor = scale_factor
@@ -79,8 +87,22 @@ class DiffusionEngine(nn.Module):
                                                self.en_and_decode_n_samples_a_time, overlap)
         return _decode_first_stage(dec.runtime(z.device), z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap)
 
-    def encode_first_stage(self, x):
-        raise NotImplementedError("the VAE encoder is outside the B200 hot path (SURVEY.md §8f)")
+    @torch.no_grad()
+    def encode_first_stage(self, x, noise: Optional[torch.Tensor] = None, sample: bool = True):
+        """diffusion.py:183-195.  Needs ``encoder_config`` (experimental B200 encoder).  The reference samples the
+        posterior with device RNG (DiagonalGaussianRegularizer, sample=True): pass ``noise`` for a reproducible draw,
+        ``sample=False`` for the mode."""
+        enc = getattr(self.first_stage_model, "encoder", None)
+        if enc is None:
+            raise NotImplementedError("the VAE encoder is outside the B200 hot path (SURVEY.md §8f); add encoder_config")
+        from .vae import Encoder, encode_first_stage as _encode_first_stage
+        if not isinstance(enc, Encoder):
+            raise NotImplementedError("encode_first_stage needs vista_b200.vae.Encoder as encoder_config.target")
+        rt = enc.runtime(x.device)
+        if sample and noise is None:
+            d = 2 ** (len(rt.cfg.ch_mult) - 1)
+            noise = torch.randn(x.shape[0], rt.cfg.z_channels, x.shape[2] // d, x.shape[3] // d, device=x.device)
+        return _encode_first_stage(rt, x, self.scale_factor, self.en_and_decode_n_samples_a_time, noise if sample else None)
 
     @torch.no_grad()
     def sample(self, cond: Dict, cond_frame=None, uc: Union[Dict, None] = None, N: int = 25,

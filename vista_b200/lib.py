@@ -109,6 +109,7 @@ SIGNATURES = {
     "b200v_conv3x3_small_cin": [_P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_conv3x3_small_cout": [_P, _I64, _I32, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "b200v_im2col_s2": [_P, _I64, _P, _I32, _I32, _I32, _I32, _P],
+    "b200v_im2col_s2_asym": [_P, _I64, _P, _I32, _I32, _I32, _I32, _P],
     "b200v_upsample2x": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_timestep_embedding": [_P, _I32, _I32, _F, _P, _I64, _P],
     "b200v_blend_emb": [_P, _P, _P, _P, _P, _P, _I32, _I32, _P],

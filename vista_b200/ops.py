@@ -329,6 +329,16 @@ def im2col_s2(x, out, NB: int, H: int, W: int, Cc: int):
     return out
 
 
+def im2col_s2_asym(x, out, NB: int, H: int, W: int, Cc: int):
+    """VAE-encoder Downsample gather (zero pad right / bottom only)."""
+    _count(1)
+    _prof_begin("other", "im2col_s2_asym", 0.0, 0.0)
+    _lib.check(_lib.load().b200v_im2col_s2_asym(x.data_ptr(), x.stride(0), out.data_ptr(), NB, H, W, Cc, _stream()),
+               "b200v_im2col_s2_asym")
+    _prof_end()
+    return out
+
+
 def upsample2x(x, out, NB: int, H: int, W: int, Cc: int):
     _count(1)
     _prof_begin("other", "upsample2x", 0.0, 0.0)

@@ -200,6 +200,168 @@ def decode_first_stage(rt: DecoderRuntime, z: torch.Tensor, scale_factor: float 
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# VAE encoder (the next row).  Host executor over the validated kernels (tap-GEMM, GroupNorm,
+# GEMM-softmax-GEMM attention) plus one new gather (b200v_im2col_s2_asym).  EXPERIMENTAL: written against the pinned
+# oracle (tests/test_oracle_golden.py::test_encoder_matches_reference) but not yet run on hardware; its GPU test is
+# opt-in (VISTA_B200_TEST_ENCODER=1) until it has been.
+# ---------------------------------------------------------------------------------------------------------------
+class EncoderRuntime(DecoderRuntime):
+    """``Encoder.forward`` (vwm/modules/diffusionmodules/model.py:527-557): conv_in, per level ResnetBlocks
+    (model.py:116-135, temb = None) + Downsample (model.py:69-83), mid (res, attn, res), GN, swish, conv_out."""
+
+    def __init__(self, cfg, sd: Dict[str, torch.Tensor], device):
+        from .spec import build_encoder_plan
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.levels, self.mid_ch = build_encoder_plan(cfg)
+        self._bufs = {}
+        self._sd = sd
+        self._pack()
+        self._sd = None
+
+    def _pack(self):
+        self.n_gn = 0
+        self.res = {}
+
+        def pack_res(rb: DecResBlockSpec):
+            p = rb.prefix
+            self.res[p] = dict(spec=rb, gn1=self._norm(f"{p}.norm1"), conv1=self._lin(f"{p}.conv1"),
+                               gn2=self._norm(f"{p}.norm2"), conv2=self._lin(f"{p}.conv2"),
+                               skip=self._lin(f"{p}.nin_shortcut") if rb.has_skip else None, gn_idx=self.n_gn)
+            self.n_gn += 2
+
+        self.conv_in_w, self.conv_in_b = self._f32("conv_in.weight"), self._f32("conv_in.bias")
+        self.downs = {}
+        for blocks, down, ch in self.levels:
+            for rb in blocks:
+                pack_res(rb)
+            if down is not None:
+                self.downs[down] = self._lin(down)          # [C, 9 C] tap-major: K order of the im2col gather
+        pack_res(DecResBlockSpec("mid.block_1", self.mid_ch, self.mid_ch))
+        a, sd = "mid.attn_1", self._sd
+        self.attn = dict(norm=self._norm(f"{a}.norm"), q=self._lin(f"{a}.q"), k=self._lin(f"{a}.k"),
+                         v_w=conv_weight_to_taps(sd[f"{a}.v.weight"].detach().to(self.dev, torch.float32)).to(torch.float16).contiguous(),
+                         v_b=self._f32(f"{a}.v.bias"), proj=self._lin(f"{a}.proj_out"), gn_idx=self.n_gn)
+        self.n_gn += 1
+        pack_res(DecResBlockSpec("mid.block_2", self.mid_ch, self.mid_ch))
+        self.norm_out = self._norm("norm_out")
+        self.norm_out_idx = self.n_gn
+        self.n_gn += 1
+        ow = conv_weight_to_taps(self._f32("conv_out.weight"))          # 2 z_channels = 8 output channels
+        assert ow.shape[0] <= 8
+        w8 = torch.zeros(8, ow.shape[1], dtype=torch.float16, device=self.dev)
+        w8[: ow.shape[0]] = ow.to(torch.float16)
+        b8 = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        b8[: ow.shape[0]] = self._f32("conv_out.bias")
+        self.out_conv = Lin(w8.contiguous(), b8, 32)
+        self.n_moments = ow.shape[0]
+
+    def _enc_resblock(self, L, x, n, h, w, name):
+        rb: DecResBlockSpec = L["spec"]
+        hw, M, gi = h * w, n * h * w, L["gn_idx"]
+        a1 = self._gn(x, self.buf("e.a1", M, rb.cin), n, hw, L["gn1"], 1e-6, gi)
+        h1 = self.gemm(a1, L["conv1"], self.buf("e.h1", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, n))
+        a2 = self._gn(h1, self.buf("e.a2", M, rb.cout), n, hw, L["gn2"], 1e-6, gi + 1)
+        xs = x if L["skip"] is None else self.gemm(x, L["skip"], self.buf("e.xs", M, rb.cout))
+        return self.gemm(a2, L["conv2"], self.buf(name, M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, n), res1=xs)
+
+    def forward(self, x_tokens: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+        """x_tokens: [(n h w), 8] fp16 image rows (channels >= in_channels zero) -> moments [(n h/8 w/8), 8] fp32
+        (mean | logvar columns)."""
+        cfg = self.cfg
+        if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] < n:
+            self.gn_stats = torch.zeros(self.n_gn, n, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+            self.gn_ws = ops.GNWorkspace(self.dev)
+        self.gn_ws.reserve(ops.groupnorm_scratch(n, h * w, cfg.num_groups))
+        x = ops.conv3x3_small_cin(x_tokens, cfg.in_channels, self.conv_in_w, self.conv_in_b,
+                                  self.buf("e.in", n * h * w, cfg.ch), n, h, w)
+        for blocks, down, ch in self.levels:
+            for bi, rb in enumerate(blocks):
+                x = self._enc_resblock(self.res[rb.prefix], x, n, h, w, f"e.r{bi % 2}")
+            if down is not None:
+                ho, wo = (h - 2) // 2 + 1, (w - 2) // 2 + 1
+                col = ops.im2col_s2_asym(x, self.buf("e.col", n * ho * wo, 9 * ch), n, h, w, ch)
+                h, w = ho, wo
+                x = self.gemm(col, self.downs[down], self.buf("e.down", n * h * w, ch))
+        x = self._enc_resblock(self.res["mid.block_1"], x, n, h, w, "e.m0")
+        x = self._attn(x, n, h, w)
+        x = self._enc_resblock(self.res["mid.block_2"], x, n, h, w, "e.m1")
+        M = n * h * w
+        a = ops.groupnorm(x, self.buf("e.a1", M, self.mid_ch), n, h * w, self.norm_out[0], self.norm_out[1], 1e-6,
+                          True, self.gn_stats[self.norm_out_idx, :n], groups=cfg.num_groups, ws=self.gn_ws)
+        return self.gemm(a, self.out_conv, self.buf("e.y", M, 8, torch.float32), taps=ops.TAPS_3X3, geom=(w, h, n))
+
+
+def encode_first_stage(rt: EncoderRuntime, x: torch.Tensor, scale_factor: float = 0.18215,
+                       n_samples: Optional[int] = None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DiffusionEngine.encode_first_stage (vwm/models/diffusion.py:183-195) over AutoencodingEngine.encode with the
+    DiagonalGaussianRegularizer (autoencoder.py:190-203, regularizers/__init__.py:30-40, distributions.py:25-36):
+    x (n,3,H,W) fp32 -> z (n,4,H/8,W/8) fp32 = (mean + exp(0.5 clamp(logvar,-30,20)) * noise) * scale_factor; the
+    reference draws `noise` from the device RNG — pass it in for reproducible parity, None gives the mode."""
+    n_all, cin, H, W = x.shape
+    n_samples = n_all if n_samples is None else n_samples
+    down = 2 ** (len(rt.cfg.ch_mult) - 1)
+    zc = rt.cfg.z_channels
+    out = torch.empty(n_all, zc, H // down, W // down, dtype=torch.float32, device=x.device)
+    for i in range(0, n_all, n_samples):
+        xs = x[i:i + n_samples].float().contiguous()
+        n = xs.shape[0]
+        tok = rt.buf("e.x", n * H * W, 8)
+        tok.zero_()
+        ops.nchw_to_tokens(xs, tok, n, cin, H, W)
+        mom_tok = rt.forward(tok, n, H, W)
+        mom = torch.empty(n, 8, H // down, W // down, dtype=torch.float32, device=x.device)
+        ops.tokens_to_nchw(mom_tok, mom, n, 8, H // down, W // down)
+        mean, logvar = mom[:, :zc], mom[:, zc:2 * zc]
+        z = mean if noise is None else mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise[i:i + n].to(mean)
+        out[i:i + n] = z * scale_factor
+    return out
+
+
+class Encoder(nn.Module):
+    """``encoder_config.target`` stand-in for vwm.modules.diffusionmodules.model.Encoder: same keywords, same
+    ``state_dict`` keys, ``forward(x)`` -> (n, 2 z_channels, H/8, W/8) moments.  EXPERIMENTAL (see EncoderRuntime)."""
+
+    def __init__(self, *, ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions=(), dropout=0.0, resamp_with_conv=True,
+                 in_channels=3, resolution=256, z_channels=4, double_z=True, use_linear_attn=False, attn_type="vanilla",
+                 **ignore_kwargs):
+        super().__init__()
+        from .spec import EncoderConfig, encoder_param_specs
+        bad = [k for k, v in dict(attn_resolutions=len(list(attn_resolutions)) != 0, dropout=dropout != 0.0,
+                                  resamp_with_conv=not resamp_with_conv, use_linear_attn=use_linear_attn,
+                                  attn_type=attn_type != "vanilla", double_z=not double_z).items() if v]
+        if bad:
+            raise NotImplementedError(f"vista_b200.Encoder: unsupported option(s) {bad}")
+        self.b200_config = EncoderConfig(ch=ch, in_channels=in_channels, ch_mult=tuple(ch_mult),
+                                         num_res_blocks=num_res_blocks, z_channels=z_channels, double_z=double_z)
+        register_param_tree(self, encoder_param_specs(self.b200_config))
+        self._runtime = None
+        self.register_load_state_dict_post_hook(lambda module, keys: setattr(module, "_runtime", None))
+
+    def _apply(self, fn, *args, **kwargs):
+        self._runtime = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def runtime(self, device) -> EncoderRuntime:
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("vista_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self._runtime is None:
+            self._runtime = EncoderRuntime(self.b200_config, self.state_dict(), device)
+        return self._runtime
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        rt = self.runtime(x.device)
+        n, cin, H, W = x.shape
+        down = 2 ** (len(rt.cfg.ch_mult) - 1)
+        tok = rt.buf("e.x", n * H * W, 8)
+        tok.zero_()
+        ops.nchw_to_tokens(x.float().contiguous(), tok, n, cin, H, W)
+        mom_tok = rt.forward(tok, n, H, W)
+        mom = torch.empty(n, 8, H // down, W // down, dtype=torch.float32, device=x.device)
+        ops.tokens_to_nchw(mom_tok, mom, n, 8, H // down, W // down)
+        return mom[:, : rt.n_moments]
+
+
 def _decode_chunks(F_: int, n_samples: int, overlap: int):
     """Chunk plan of decode_first_stage (vwm/models/diffusion.py:150-180): (first input frame, frame count,
     first output frame, overlapping frames that are averaged with the previous chunk's output)."""
