@@ -44,8 +44,11 @@ def gemm(a, w, out, *, taps=((0, 0),), geom=None, bias=None, rowvec=None, rv_div
         acc = acc + _f(rowvec)[rows][:, :N]
     if act == 1:
         acc = F.silu(acc)
-    elif act == 2:
-        raise NotImplementedError("GEGLU is not needed by the VAE executors")
+    elif act == 2:                               # value | gate halves per tile of tile_n columns (weights.permute_geglu)
+        tn = tile_n if tile_n is not None else N
+        hh = tn // 2
+        t = acc.reshape(tokens, N // tn, 2, hh)
+        acc = (t[:, :, 0] * F.gelu(t[:, :, 1])).reshape(tokens, N // 2)
     if res1 is not None:
         acc = acc + s_res1 * _f(res1)
     if res2 is not None:
@@ -133,18 +136,148 @@ def time_mix_small(x, w, bias, out, blend, T, HW, Cc, out_frame0=0, skip_frames=
     return out
 
 
+def groupnorm_sums(x, frames, tokens_per_frame, Cc, sums, frames_per_stat, groups=32, ws=None):
+    xs = x[:, :Cc].double().reshape(frames // frames_per_stat, frames_per_stat * tokens_per_frame, groups, Cc // groups)
+    sums.copy_(torch.stack([xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))], dim=-1).reshape(sums.shape))
+    return sums
+
+
+def groupnorm_finalize_apply(x, y, frames, tokens_per_frame, gamma, beta, eps, silu, sums, count, stats, frames_per_stat,
+                             groups=32):
+    C = gamma.numel()
+    n_stat = frames // frames_per_stat
+    sm = sums.reshape(n_stat, groups, 2)
+    mean = sm[..., 0] / count
+    var = (sm[..., 1] / count - mean * mean).clamp_min(0.0)
+    xs = _f(x[:, :C]).reshape(n_stat, frames_per_stat * tokens_per_frame, groups, C // groups)
+    o = (xs - mean.float()[:, None, :, None]) * torch.rsqrt(var.float() + eps)[:, None, :, None]
+    o = o.reshape(-1, C) * _f(gamma) + _f(beta)
+    if silu:
+        o = F.silu(o)
+    y.copy_(o.to(y.dtype))
+    return y
+
+
+def layernorm(x, y, gamma, beta, eps=1e-5, addvec=None, av_div=1, av_mod=1):
+    C = gamma.numel()
+    v = _f(x[:, :C])
+    if addvec is not None:
+        rows = (torch.arange(v.shape[0]) // av_div) % av_mod
+        v = v + _f(addvec)[rows][:, :C]
+    y.copy_(F.layer_norm(v, (C,), _f(gamma), _f(beta), eps).to(y.dtype))
+    return y
+
+
+def attention_spatial(q, k, v, out, frames, seq, heads, impl=None):
+    def sp(t):
+        return _f(t).reshape(frames, seq, heads, 64).permute(0, 2, 1, 3)
+    o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v))
+    out.copy_(o.permute(0, 2, 1, 3).reshape(frames * seq, heads * 64).to(out.dtype))
+    return out
+
+
+def attention_temporal(q, k, v, out, nb, T, S, heads):
+    def tp(t):                                   # tokens (b, t, s) -> (b, s, head, t, 64)
+        return _f(t).reshape(nb, T, S, heads, 64).permute(0, 2, 3, 1, 4)
+    o = F.scaled_dot_product_attention(tp(q), tp(k), tp(v))
+    out.copy_(o.permute(0, 3, 1, 2, 4).reshape(nb * T * S, heads * 64).to(out.dtype))
+    return out
+
+
+def attention_temporal_sharded(q, k, v, out, nb, Tq, T, S, heads, kv_frame_tok):
+    C = heads * 64
+    rows = (kv_frame_tok.reshape(nb, T, 1) + torch.arange(S).reshape(1, 1, S)).reshape(-1)      # (b, t, s) -> gathered row
+    kk = _f(k)[rows].reshape(nb, T, S, heads, 64).permute(0, 2, 3, 1, 4)
+    vv = _f(v)[rows].reshape(nb, T, S, heads, 64).permute(0, 2, 3, 1, 4)
+    qq = _f(q).reshape(nb, Tq, S, heads, 64).permute(0, 2, 3, 1, 4)
+    o = F.scaled_dot_product_attention(qq, kk, vv)
+    out.copy_(o.permute(0, 3, 1, 2, 4).reshape(nb * Tq * S, C).to(out.dtype))
+    return out
+
+
+def timestep_embedding(t, out, dim, max_period=10000.0):
+    half = dim // 2
+    freq = torch.exp(-torch.log(torch.tensor(float(max_period))) * torch.arange(half, dtype=torch.float32) / half)
+    a = _f(t).reshape(-1, 1) * freq
+    out[:, :dim] = torch.cat([torch.cos(a), torch.sin(a)], dim=1).to(out.dtype)
+    return out
+
+
+def blend_emb(e_plain, e_cond, label, mask, emb, silu_emb):
+    m = torch.zeros(e_plain.shape[0], 1) if mask is None else _f(mask).reshape(-1, 1)
+    e = _f(e_plain) * (1.0 - m)
+    if e_cond is not None:
+        e = e + _f(e_cond) * m
+    if label is not None:
+        e = e + _f(label)
+    if emb is not None:
+        emb.copy_(e)
+    if silu_emb is not None:
+        silu_emb.copy_(F.silu(e).to(silu_emb.dtype))
+
+
+def im2col_s2(x, out, NB, H, W, Cc):
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    img = F.pad(x[:, :Cc].reshape(NB, H, W, Cc), (0, 0, 1, 2, 1, 2))
+    parts = [img[:, kh:kh + 2 * Ho:2, kw:kw + 2 * Wo:2] for kh in range(3) for kw in range(3)]
+    out.copy_(torch.cat(parts, dim=-1).reshape(NB * Ho * Wo, 9 * Cc))
+    return out
+
+
+def sampler_prepare(x, cond_frame, mask, concat_u, concat_c, sigmas, step_idx, unet_in, c_noise, T, h, w):
+    sigma = float(sigmas[int(step_idx[0])])
+    c_in = (sigma * sigma + 1.0) ** -0.5
+    if mask is not None and cond_frame is not None:
+        m = _f(mask).reshape(T, 1, 1, 1)
+        x.copy_(x * (1.0 - m) + cond_frame * m)
+    if c_noise is not None:
+        c_noise.fill_(0.25 * float(torch.log(torch.tensor(sigma))))
+    xs = (x * c_in).permute(0, 2, 3, 1).reshape(T * h * w, 4)
+    zu = torch.zeros_like(xs) if concat_u is None else concat_u.permute(0, 2, 3, 1).reshape(T * h * w, 4)
+    zc = torch.zeros_like(xs) if concat_c is None else concat_c.permute(0, 2, 3, 1).reshape(T * h * w, 4)
+    unet_in[: T * h * w, :8] = torch.cat([xs, zu], 1).to(unet_in.dtype)
+    unet_in[T * h * w:, :8] = torch.cat([xs, zc], 1).to(unet_in.dtype)
+
+
+def sampler_update(x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_steps, T, h, w):
+    step = int(step_idx[0])
+    sigma, sigma_next = float(sigmas[step]), float(sigmas[step + 1])
+    c_skip, c_out = 1.0 / (sigma * sigma + 1.0), -sigma * (sigma * sigma + 1.0) ** -0.5
+    hw = h * w
+    nu = _f(net_out[: T * hw, :4]).reshape(T, h, w, 4).permute(0, 3, 1, 2)
+    nc = _f(net_out[T * hw:, :4]).reshape(T, h, w, 4).permute(0, 3, 1, 2)
+    du, dc = nu * c_out + x * c_skip, nc * c_out + x * c_skip
+    den = du + _f(scales).reshape(T, 1, 1, 1) * (dc - du)
+    xn = x + (x - den) / sigma * (sigma_next - sigma)
+    if step + 1 == num_steps and mask is not None and cond_frame is not None:
+        m = _f(mask).reshape(T, 1, 1, 1)
+        xn = xn * (1.0 - m) + cond_frame * m
+    x.copy_(xn)
+    step_idx += 1
+
+
 _PATCHED = ["gemm", "GNWorkspace", "groupnorm_scratch", "groupnorm", "conv3x3_small_cin", "im2col_s2_asym", "upsample2x",
-            "softmax_rows", "nchw_to_tokens", "tokens_to_nchw", "time_mix_small"]
+            "softmax_rows", "nchw_to_tokens", "tokens_to_nchw", "time_mix_small", "groupnorm_sums",
+            "groupnorm_finalize_apply", "layernorm", "attention_spatial", "attention_temporal",
+            "attention_temporal_sharded", "timestep_embedding", "blend_emb", "im2col_s2", "sampler_prepare",
+            "sampler_update"]
+_NOT_TAPED = {"GNWorkspace", "groupnorm_scratch"}
 
 
 @contextlib.contextmanager
 def patched_ops():
-    """Swap the emulations into vista_b200.ops for the duration of the block."""
-    from vista_b200 import ops
+    """Swap the emulations into vista_b200.ops for the duration of the block.  Every emulated launch goes through
+    lib.tape_host, so that a launch tape recorded by the executors replays them like real C-ABI calls."""
+    from vista_b200 import lib, ops
+
+    def taped(fn):
+        def call(*a, **k):
+            return lib.tape_host(lambda: fn(*a, **k))
+        return call
     saved = {k: getattr(ops, k) for k in _PATCHED}
     try:
         for k in _PATCHED:
-            setattr(ops, k, globals()[k])
+            setattr(ops, k, globals()[k] if k in _NOT_TAPED else taped(globals()[k]))
         yield
     finally:
         for k, v in saved.items():

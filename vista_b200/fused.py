@@ -86,9 +86,10 @@ class _LoopState:
         graph: the whole step, or prepare + UNet in CFG-split mode (the pair exchange and the update stay eager)."""
         if not USE_GRAPH:
             return lambda: self.one_step(rt, num_steps)
-        if getattr(rt, "group", None) is not None and not USE_TAPE:
+        # NB: `rt.group is None` also names the DEFAULT process group; the runtime says whether its step holds collectives
+        if getattr(rt, "has_collectives", False) and not USE_TAPE:
             return lambda: self.one_step(rt, num_steps)
-        if getattr(rt, "group", None) is not None:
+        if getattr(rt, "has_collectives", False):
             # collectives inside the UNet: no graph; the first call records the step's C-ABI calls and host-side
             # collectives on a launch tape (vista_b200.lib), later calls replay it without the Python layers above
             def run_taped():

@@ -125,9 +125,13 @@ class _RuntimeOwner:
     def _rt_invalidate(self):
         self._runtime, self._runtime_key, self._cond_cache = None, None, None
 
-    def _rt_get(self, model: nn.Module, num_frames: int, device) -> UNetRuntime:
+    @staticmethod
+    def _require_cuda(device):
         if not torch.cuda.is_available() or torch.device(device).type != "cuda":
             raise RuntimeError("vista_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+
+    def _rt_get(self, model: nn.Module, num_frames: int, device) -> UNetRuntime:
+        self._require_cuda(device)
         key = (num_frames, str(device), id(model), self.frame_sharded)
         if self._runtime is None or self._runtime_key != key:
             cfg = _infer_config(model)

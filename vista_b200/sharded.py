@@ -66,6 +66,8 @@ class HaloExchange:
 
 
 class ShardedUNetRuntime(UNetRuntime):
+    has_collectives = True        # its step issues NCCL calls: never CUDA-graph-captured, replayed from the launch tape
+
     def __init__(self, cfg: UNetConfig, sd: Dict[str, torch.Tensor], device, num_frames: int = 25, group=None):
         self.group = group
         self.world = dist.get_world_size(group)

@@ -48,6 +48,7 @@ def padded_input_rows(rows: int, device) -> torch.Tensor:
 
 class UNetRuntime:
     """Device-resident, repacked VideoUNet.  One instance per (weights, num_frames)."""
+    has_collectives = False       # a step is a fixed sequence of local launches: CUDA-graph capturable
 
     def __init__(self, cfg: UNetConfig, sd: Dict[str, torch.Tensor], device, num_frames: int = 25):
         self.cfg, self.dev, self.T = cfg, torch.device(device), num_frames
