@@ -309,7 +309,8 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         # The measurement is complete and printed.  Leave without the NCCL / interpreter teardown: a multi-rank process
-        # that lingers there (observed once after a taped frame-sharded run) would hold the whole launch hostage.
+        # that lingers there would hold the whole launch hostage (seen once, when a frames-only step on the default
+        # process group had been CUDA-graph-captured with its NCCL calls inside; that path now uses the launch tape).
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
