@@ -141,3 +141,51 @@ def test_sharded_sampler_on_emulated_ops(world, cfg_split):
         assert np.array_equal(out, res[0][1]), f"rank {rank} holds a different latent"
         r = rel_l2(torch.from_numpy(out), ref)
         assert r < 5e-3, (rank, r)
+
+
+def _pdecode_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from fake_ops import patched_ops as patched
+        from helpers import decoder_weights as dw, to_t as tt
+        from vista_b200 import synth as sy
+        from vista_b200.vae import DecoderRuntime, decode_first_stage, decode_first_stage_parallel
+        cfg, sd = dw("tiny")
+        z = torch.from_numpy(sy.normal(9, "decfs.z", (25, cfg.z_channels, 8, 16), std=0.18215))
+        with patched(), torch.no_grad():
+            rt = DecoderRuntime(cfg, tt(sd), "cpu")
+            serial = decode_first_stage(rt, z)
+            par = decode_first_stage_parallel(rt, z)
+            small = decode_first_stage_parallel(rt, z, n_samples=8, overlap=2)      # 4 chunks over the ranks
+            small_serial = decode_first_stage(rt, z, n_samples=8, overlap=2)
+        q.put((rank, bool(torch.equal(serial, par)), bool(torch.equal(small, small_serial)), par.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_parallel_decode_on_emulated_ops_three_ranks():
+    """decode_first_stage_parallel with more ranks than chunks (3 ranks, 2 chunks) and with more chunks than ranks
+    (4 chunks): bit-identical to the serial chunked decode on every rank, and equal to the reference fixture."""
+    import os
+    import torch.multiprocessing as mp
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 37500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_pdecode_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=240) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = torch.from_numpy(golden("decode_first_stage_tiny")["out"])
+    for rank, same, same_small, out in res:
+        assert same and same_small, rank
+        assert rel_l2(torch.from_numpy(out), ref) < 5e-3
