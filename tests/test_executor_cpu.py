@@ -189,3 +189,45 @@ def test_parallel_decode_on_emulated_ops_three_ranks():
     for rank, same, same_small, out in res:
         assert same and same_small, rank
         assert rel_l2(torch.from_numpy(out), ref) < 5e-3
+
+
+@pytest.mark.parametrize("name,steps,guider,n_cond", [("sampler_tiny_cfg", 4, "VanillaCFG", 1),
+                                                     ("sampler_tiny_triangle", 3, "TrianglePredictionGuider", 3)])
+def test_fused_and_generic_sampler_on_emulated_ops(name, steps, guider, n_cond, monkeypatch):
+    """Single-rank sampler host logic on emulated operators: the fused loop (device-side step index, scale vector,
+    conditioning-frame re-imposition) and the generic loop through B200Wrapper both reproduce the real reference's
+    samples; same cases as tests/test_sampler_gpu.py."""
+    from helpers import unet_weights
+    from vista_b200 import fused as fused_mod
+    from vista_b200.diffusion import B200Denoiser, Denoiser, EulerEDMSampler
+    from vista_b200.modules import B200Wrapper, VideoUNet
+    monkeypatch.setattr(fused_mod, "USE_GRAPH", False)          # no CUDA graphs on the emulated path
+    cfg, sd = unet_weights("tiny")
+    unet = VideoUNet(in_channels=cfg.in_channels, model_channels=cfg.model_channels, out_channels=cfg.out_channels,
+                     num_res_blocks=cfg.num_res_blocks, attention_resolutions=list(cfg.attention_resolutions),
+                     channel_mult=list(cfg.channel_mult), num_head_channels=64, num_classes="sequential",
+                     context_dim=cfg.context_dim, adm_in_channels=cfg.adm_in_channels, extra_ff_mix_layer=True,
+                     use_spatial_context=True, merge_strategy="learned_with_images", video_kernel_size=[3, 1, 1],
+                     use_linear_in_transformer=True, action_control=True)
+    unet.load_state_dict(to_t(sd), strict=True)
+    net = B200Wrapper(unet)
+    net._require_cuda = unet._require_cuda = lambda device: None
+    den = Denoiser({"target": "vista_b200.diffusion.VScalingWithEDMcNoise"}, num_frames=25)
+    g = {"target": "vista_b200.diffusion.VanillaCFG", "params": {"scale": 2.5}} if guider == "VanillaCFG" else \
+        {"target": "vista_b200.diffusion.TrianglePredictionGuider", "params": {"max_scale": 2.5, "num_frames": 25}}
+    smp = EulerEDMSampler(num_steps=steps, device="cpu", s_churn=0.0, s_tmin=0.0, s_tmax=999.0, s_noise=1.0, verbose=False,
+                          discretization_config={"target": "vista_b200.diffusion.EDMDiscretization",
+                                                 "params": {"sigma_min": 0.002, "sigma_max": 700.0, "rho": 7.0}},
+                          guider_config=g)
+    c, uc = synth.synth_conditioning(7, 25, 8, 16, trajectory=True, context_dim=cfg.context_dim, adm=cfg.adm_in_channels)
+    noise, z, mask = synth.synth_latents(7, 25, 8, 16)
+    mask[:n_cond] = 1.0
+    td = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    zt, mt = torch.from_numpy(z), torch.from_numpy(mask)
+    ref = torch.from_numpy(golden(name)["sample"])
+    with patched_ops(), torch.no_grad():
+        fused = smp(B200Denoiser(den, net), torch.from_numpy(noise).clone(), td(c), uc=td(uc), cond_frame=zt, cond_mask=mt)
+        generic = smp(lambda x, s, cc, m: den(net, x, s, cc, m), torch.from_numpy(noise).clone(), td(c), uc=td(uc),
+                      cond_frame=zt, cond_mask=mt)
+    assert rel_l2(fused, ref) < 5e-3 and rel_l2(generic, ref) < 5e-3
+    assert torch.equal(fused[:n_cond], zt[:n_cond])              # conditioning frames re-imposed (sampling.py:122-123)
