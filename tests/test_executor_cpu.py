@@ -231,3 +231,53 @@ def test_fused_and_generic_sampler_on_emulated_ops(name, steps, guider, n_cond, 
                       cond_frame=zt, cond_mask=mt)
     assert rel_l2(fused, ref) < 5e-3 and rel_l2(generic, ref) < 5e-3
     assert torch.equal(fused[:n_cond], zt[:n_cond])              # conditioning frames re-imposed (sampling.py:122-123)
+
+
+def _sdecode_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from fake_ops import patched_ops as patched
+        from helpers import decoder_weights as dw, to_t as tt
+        from vista_b200 import synth as sy
+        from vista_b200.sharded import ShardedDecoderRuntime, decode_first_stage_sharded
+        from vista_b200.vae import DecoderRuntime, decode_first_stage
+        cfg, sd = dw("tiny")
+        z = torch.from_numpy(sy.normal(9, "decfs.z", (25, cfg.z_channels, 8, 16), std=0.18215))
+        with patched(), torch.no_grad():
+            serial = decode_first_stage(DecoderRuntime(cfg, tt(sd), "cpu"), z)
+            sharded = decode_first_stage_sharded(ShardedDecoderRuntime(cfg, tt(sd), "cpu"), z)
+        q.put((rank, serial.numpy(), sharded.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_frame_sharded_decode_on_emulated_ops(world):
+    """Experimental frame-sharded decode (sharded.ShardedDecoderRuntime): 14-frame chunks over 2 / 4 ranks (interior
+    ranks, one- and multi-frame shards) reproduce the serial chunked decode up to the re-association of the temporal
+    GroupNorm sums, on every rank, and match the reference fixture."""
+    import os
+    import numpy as np
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 39500 + (os.getpid() + 11 * world) % 2000
+    procs = [ctx.Process(target=_sdecode_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=240) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = torch.from_numpy(golden("decode_first_stage_tiny")["out"])
+    for rank, serial, sharded in res:
+        assert np.array_equal(sharded, res[0][2]), "every rank must hold the same clip"
+        r1 = rel_l2(torch.from_numpy(sharded), torch.from_numpy(serial))
+        assert r1 < 2e-3, (rank, r1)
+        assert rel_l2(torch.from_numpy(sharded), ref) < 5e-3

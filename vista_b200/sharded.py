@@ -202,3 +202,163 @@ def gather_latent(x_local: torch.Tensor, num_frames: int, group=None) -> torch.T
     dist.all_gather_into_tensor(out, buf, group=group)
     parts = out.reshape(world, pad, *x_local.shape[1:])
     return torch.cat([parts[r, : b - a] for r, (a, b) in enumerate(shards)], dim=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Frame-sharded VAE decode (EXPERIMENTAL, opt-in: VISTA_B200_SHARDED_DECODE=1).  The frames of every decode chunk are
+# spread over the ranks with the same three mechanisms as the UNet: the temporal GroupNorm's sums are all-reduced, the
+# (3,1,1) convolutions get one-frame halo corrections, and the closing 3-tap time mix (AE3DConv, temporal_ae.py:90-97)
+# reads one halo frame of its 3-channel input on each side.  Host-side orchestration only — no new kernel; validated on
+# emulated operators under gloo (tests/test_executor_cpu.py), not yet on hardware.
+# ---------------------------------------------------------------------------------------------------------------
+from .vae import DecoderRuntime, _decode_chunks      # noqa: E402  (kept next to its only user)
+
+
+class ShardedDecoderRuntime(DecoderRuntime):
+    def __init__(self, cfg, sd, device, group=None):
+        super().__init__(cfg, sd, device)
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._to_global = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
+        self._tap_w: Dict[int, tuple] = {}
+        self.T_full, self.prev, self.next = 0, None, None
+
+    def _set_chunk(self, n_frames: int):
+        """Frame shards of an n_frames chunk; ranks beyond the frame count own nothing (and only take part in the
+        collectives with zero contributions)."""
+        self.T_full = n_frames
+        self.shards = frame_shards(n_frames, min(self.world, n_frames))
+        self.active = self.rank < len(self.shards)
+        self.t0, self.t1 = self.shards[self.rank] if self.active else (0, 0)
+        last = len(self.shards) - 1
+        self.prev = self._to_global(self.rank - 1) if self.active and self.rank > 0 else None
+        self.next = self._to_global(self.rank + 1) if self.active and self.rank < last else None
+
+    # temporal GroupNorm: one statistic over ALL frames of the chunk
+    def _gn(self, x, y, T, hw, norm, eps, idx, fps=1):
+        if fps == 1:
+            return super()._gn(x, y, T, hw, norm, eps, idx, fps)
+        Cc, G = norm[0].numel(), self.cfg.num_groups
+        sums = self.buf("gn.sums", G, 2, torch.float64)
+        ops.groupnorm_sums(x, T, hw, Cc, sums, T, groups=G, ws=self.gn_ws)
+        dist.all_reduce(sums, group=self.group)
+        count = float(Cc // G) * hw * self.T_full
+        return ops.groupnorm_finalize_apply(x, y, T, hw, norm[0], norm[1], eps, True, sums, count,
+                                            self.gn_stats[idx, :1], T, groups=G)
+
+    def _tap_weights(self, lin: Lin):
+        key = lin.w.data_ptr()
+        tw = self._tap_w.get(key)
+        if tw is None:
+            Cc = lin.w.shape[1] // 3
+            tw = (Lin(lin.w[:, :Cc].contiguous(), None, lin.tile_n), Lin(lin.w[:, 2 * Cc:].contiguous(), None, lin.tile_n))
+            self._tap_w[key] = tw
+        return tw
+
+    def _tconv(self, a, lin: Lin, out, T: int, hw: int, **epi):
+        Cc = a.shape[1]
+        send_first, send_last = self.buf("halo.sf", hw, Cc), self.buf("halo.sl", hw, Cc)
+        recv_prev, recv_next = self.buf("halo.rp", hw, Cc), self.buf("halo.rn", hw, Cc)
+        halo = HaloExchange(self.group, self.prev, self.next,
+                            first=(send_first, a[:hw], send_first, recv_prev),
+                            last=(send_last, a[(T - 1) * hw:T * hw], send_last, recv_next))
+        halo.start()
+        self.gemm(a, lin, out, taps=ops.TAPS_T3, geom=(hw, T, 1), **epi)
+        halo.wait()
+        s_acc = epi.get("s_acc", 1.0)
+        w0, w2 = self._tap_weights(lin)
+        if self.prev is not None:
+            o = out[:hw]
+            self.gemm(recv_prev, w0, o, s_acc=s_acc, res1=o)
+        if self.next is not None:
+            o = out[(T - 1) * hw:T * hw]
+            self.gemm(recv_next, w2, o, s_acc=s_acc, res1=o)
+        return out
+
+    def _resblock(self, L, x, T, h, w, name):
+        rb = L["spec"]
+        hw, M, gi = h * w, T * h * w, L["gn_idx"]
+        a1 = self._gn(x, self.buf("d.a1", M, rb.cin), T, hw, L["gn1"], 1e-6, gi)
+        h1 = self.gemm(a1, L["conv1"], self.buf("d.h1", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, T))
+        a2 = self._gn(h1, self.buf("d.a2", M, rb.cout), T, hw, L["gn2"], 1e-6, gi + 1)
+        xs = x if L["skip"] is None else self.gemm(x, L["skip"], self.buf("d.xs", M, rb.cout))
+        xsp = self.gemm(a2, L["conv2"], self.buf("d.xsp", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, T), res1=xs)
+        a3 = self._gn(xsp, self.buf("d.a1", M, rb.cout), T, hw, L["tgn1"], 1e-5, gi + 2, fps=T)
+        h2 = self._tconv(a3, L["tconv1"], self.buf("d.h1", M, rb.cout), T, hw)
+        a4 = self._gn(h2, self.buf("d.a2", M, rb.cout), T, hw, L["tgn2"], 1e-5, gi + 3, fps=T)
+        out = self.buf(name, M, rb.cout)
+        self._tconv(a4, L["tconv2"], out, T, hw, s_acc=L["alpha"], res1=xsp)       # xsp + alpha*(conv + bias)
+        return out
+
+    def forward_local(self, z_tokens: torch.Tensor, T: int, h: int, w: int) -> torch.Tensor:
+        """z_tokens: rows of THIS rank's T frames of the chunk -> (T, 3, 8h, 8w) fp32 frames (time mix included)."""
+        cfg = self.cfg
+        if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] < max(T, 1):
+            self.gn_stats = torch.zeros(self.n_gn, max(T, 1), cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+            self.gn_ws = ops.GNWorkspace(self.dev)
+        up_total = 2 ** (len(cfg.ch_mult) - 1)
+        self.gn_ws.reserve(ops.groupnorm_scratch(T, h * w * up_total * up_total, cfg.num_groups))
+        x = ops.conv3x3_small_cin(z_tokens, cfg.z_channels, self.conv_in_w, self.conv_in_b,
+                                  self.buf("d.in", T * h * w, self.plan.block_in), T, h, w)
+        x = self._resblock(self.res[self.plan.mid[0].prefix], x, T, h, w, "d.r0")
+        x = self._attn(x, T, h, w)
+        x = self._resblock(self.res[self.plan.mid[1].prefix], x, T, h, w, "d.r1")
+        for blocks, up, ch in self.plan.levels:
+            for bi, rb in enumerate(blocks):
+                x = self._resblock(self.res[rb.prefix], x, T, h, w, f"d.r{bi % 2}")
+            if up is not None:
+                xu = ops.upsample2x(x, self.buf("d.up", T * 4 * h * w, ch), T, h, w, ch)
+                h, w = 2 * h, 2 * w
+                x = self.gemm(xu, self.ups[up], self.buf("d.upc", T * h * w, ch), taps=ops.TAPS_3X3, geom=(w, h, T))
+        hw, M = h * w, T * h * w
+        a = ops.groupnorm(x, self.buf("d.a1", M, self.plan.final_ch), T, hw, self.norm_out[0], self.norm_out[1], 1e-6,
+                          True, self.gn_stats[self.norm_out_idx, :T], groups=cfg.num_groups, ws=self.gn_ws)
+        # 3-channel conv into the middle of a (T + 2)-frame buffer whose first / last frame are the neighbours' halos
+        y_ext = self.buf("d.yext", (T + 2) * hw, 8, torch.float32)
+        y_ext.zero_()
+        y = y_ext[hw:(T + 1) * hw]
+        self.gemm(a, self.out_conv, y, taps=ops.TAPS_3X3, geom=(w, h, T))
+        send_first, send_last = self.buf("halo.yf", hw, 8, torch.float32), self.buf("halo.yl", hw, 8, torch.float32)
+        halo = HaloExchange(self.group, self.prev, self.next,
+                            first=(send_first, y[:hw], send_first, y_ext[:hw]),
+                            last=(send_last, y[(T - 1) * hw:], send_last, y_ext[(T + 1) * hw:]))
+        halo.start()
+        halo.wait()
+        ext = torch.empty(T + 2, cfg.out_ch, h, w, dtype=torch.float32, device=self.dev)
+        ops.time_mix_small(y_ext, self.tmix_w, self.tmix_b, ext, None, T + 2, hw, cfg.out_ch, 0, 0)
+        return ext[1:T + 1]
+
+
+def decode_first_stage_sharded(rt: ShardedDecoderRuntime, z: torch.Tensor, scale_factor: float = 0.18215,
+                               n_samples: Optional[int] = 14, overlap: int = 3) -> torch.Tensor:
+    """decode_first_stage with the FRAMES of every chunk sharded over the ranks of rt.group; every rank passes the same
+    z and receives the whole clip.  Chunk / overlap rule as in the serial path (vwm/models/diffusion.py:150-180)."""
+    F_, zc, h, w = z.shape
+    n_samples = F_ if n_samples is None else n_samples
+    up = 2 ** (len(rt.cfg.ch_mult) - 1)
+    H, W = h * up, w * up
+    out = torch.empty(F_, rt.cfg.out_ch, H, W, dtype=torch.float32, device=z.device)
+    zs = (z.float() / scale_factor).contiguous()
+    chunks = _decode_chunks(F_, n_samples, overlap)
+    if any(nov > n or o0 != f0 for f0, n, o0, nov in chunks):
+        raise NotImplementedError("decode_first_stage_sharded: chunks shorter than the overlap")
+    for f0, n, o0, nov in chunks:
+        rt._set_chunk(n)
+        pad = max(b - a for a, b in rt.shards)
+        mine = torch.zeros(pad, rt.cfg.out_ch, H, W, dtype=torch.float32, device=z.device)
+        if rt.active:
+            T = rt.t1 - rt.t0
+            tok = rt.buf("d.z", T * h * w, 8)
+            tok.zero_()
+            ops.nchw_to_tokens(zs[f0 + rt.t0:f0 + rt.t1].contiguous(), tok, T, zc, h, w)
+            mine[:T] = rt.forward_local(tok, T, h, w)
+        else:                                   # more ranks than frames: join the collectives with empty hands
+            raise NotImplementedError("decode_first_stage_sharded: more ranks than frames in a chunk")
+        gathered = torch.empty(rt.world * pad, rt.cfg.out_ch, H, W, dtype=torch.float32, device=z.device)
+        dist.all_gather_into_tensor(gathered, mine, group=rt.group)
+        parts = gathered.reshape(rt.world, pad, rt.cfg.out_ch, H, W)
+        chunk = torch.cat([parts[r, : b - a] for r, (a, b) in enumerate(rt.shards)], dim=0)
+        if nov:
+            out[o0:o0 + nov] = 0.5 * (out[o0:o0 + nov] + chunk[:nov])
+        out[o0 + nov:o0 + n] = chunk[nov:]
+    return out

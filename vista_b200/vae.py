@@ -476,13 +476,22 @@ class VideoDecoder(nn.Module):
 def bench_decode(dcfg: DecoderConfig, rand_sd, dev, T: int, h: int, w: int, reps: int = 1, parallel: bool = False) -> float:
     """Seconds for one chunked decode of a T-frame clip (warm).  parallel: chunks dealt out over the ranks of the
     default process group (every rank must call; the caller takes the max over ranks)."""
+    import os
     sd = rand_sd(decoder_param_specs(dcfg))
-    rt = DecoderRuntime(dcfg, sd, dev)
+    frame_sharded = parallel and os.environ.get("VISTA_B200_SHARDED_DECODE") == "1"     # experimental, opt-in
+    if frame_sharded:
+        from .sharded import ShardedDecoderRuntime, decode_first_stage_sharded
+        rt = ShardedDecoderRuntime(dcfg, sd, dev)
+    else:
+        rt = DecoderRuntime(dcfg, sd, dev)
     z = torch.randn(T, dcfg.z_channels, h, w, device=dev) * 0.18215
     if parallel:
         import torch.distributed as dist
         dist.broadcast(z, src=0)
-    fn = (lambda: decode_first_stage_parallel(rt, z)) if parallel else (lambda: decode_first_stage(rt, z))
+    if frame_sharded:
+        fn = lambda: decode_first_stage_sharded(rt, z)
+    else:
+        fn = (lambda: decode_first_stage_parallel(rt, z)) if parallel else (lambda: decode_first_stage(rt, z))
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
