@@ -50,3 +50,23 @@ def rel_l2(a, b):
     a = a.double().flatten()
     b = b.double().flatten()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rollout(sample_fn, z, noises, T):
+    """The multi-round loop of sample_utils.do_sample (sample_utils.py:318-365) with a fixed synthetic conditioning
+    (the reference re-encodes the condition frame with CLIP / the VAE between rounds: outside the path).
+    sample_fn(noise, cond_frame, cond_mask) -> (T,4,h,w).  Returns samples_z ((rounds*(T-3)+3), 4, h, w)."""
+    rounds = len(noises)
+    init_mask, pred_mask = torch.zeros(T, device=z.device), torch.zeros(T, device=z.device)
+    init_mask[0] = 1
+    pred_mask[[0, 1, 2]] = 1
+    samples_z = torch.zeros((rounds * (T - 3) + 3,) + tuple(z.shape[1:]), device=z.device)
+    sample = sample_fn(noises[0].clone(), z, init_mask)
+    sample[0] = z[0]
+    samples_z[:T] = sample
+    for n in range(rounds - 1):
+        filled = torch.zeros_like(z)
+        filled[[0, 1, 2]] = sample[-3:]
+        sample = sample_fn(noises[n + 1].clone(), filled, pred_mask)
+        samples_z[(n + 1) * (T - 3) + 3:(n + 1) * (T - 3) + T] = sample[3:]
+    return samples_z

@@ -281,3 +281,58 @@ def test_frame_sharded_decode_on_emulated_ops(world):
         r1 = rel_l2(torch.from_numpy(sharded), torch.from_numpy(serial))
         assert r1 < 2e-3, (rank, r1)
         assert rel_l2(torch.from_numpy(sharded), ref) < 5e-3
+
+
+def test_multi_round_rollout_through_the_reference_closure_on_emulated_ops(monkeypatch):
+    """BASELINE config 4 semantics (sample_utils.py:318-365): round 1 conditioned on frame 0, later rounds on the last
+    three latents through cond_mask[[0,1,2]], TrianglePredictionGuider, results stitched into samples_z.  The sampler
+    receives the reference's own closure shape around an engine-like object and must reach the fused loop; the result
+    is compared with the same loop on the CPU oracle."""
+    from helpers import rollout, unet_weights
+    from oracle import vista_oracle as vo
+    from vista_b200 import fused as fused_mod
+    from vista_b200.diffusion import Denoiser, EulerEDMSampler
+    from vista_b200.modules import B200Wrapper, VideoUNet
+    monkeypatch.setattr(fused_mod, "USE_GRAPH", False)
+    calls = {"fused": 0}
+    real_fused = fused_mod.fused_sample
+    monkeypatch.setattr(fused_mod, "fused_sample", lambda *a, **k: (calls.__setitem__("fused", calls["fused"] + 1), real_fused(*a, **k))[1])
+    cfg, sd = unet_weights("tiny")
+    unet = VideoUNet(in_channels=cfg.in_channels, model_channels=cfg.model_channels, out_channels=cfg.out_channels,
+                     num_res_blocks=cfg.num_res_blocks, attention_resolutions=list(cfg.attention_resolutions),
+                     channel_mult=list(cfg.channel_mult), num_head_channels=64, num_classes="sequential",
+                     context_dim=cfg.context_dim, adm_in_channels=cfg.adm_in_channels, extra_ff_mix_layer=True,
+                     use_spatial_context=True, merge_strategy="learned_with_images", video_kernel_size=[3, 1, 1],
+                     use_linear_in_transformer=True, action_control=True)
+    unet.load_state_dict(to_t(sd), strict=True)
+
+    class Engine:
+        pass
+    model = Engine()
+    model.model = B200Wrapper(unet)
+    model.model._require_cuda = unet._require_cuda = lambda device: None
+    model.denoiser = Denoiser({"target": "vista_b200.diffusion.VScalingWithEDMcNoise"}, num_frames=25)
+
+    def denoiser(x, sigma, cond, cond_mask):           # sample_utils.py:314-315, verbatim shape
+        return model.denoiser(model.model, x, sigma, cond, cond_mask)
+    T, h, w, steps, rounds = 25, 8, 16, 3, 2
+    smp = EulerEDMSampler(num_steps=steps, device="cpu", s_churn=0.0, s_tmin=0.0, s_tmax=999.0, s_noise=1.0, verbose=False,
+                          discretization_config={"target": "vista_b200.diffusion.EDMDiscretization",
+                                                 "params": {"sigma_min": 0.002, "sigma_max": 700.0, "rho": 7.0}},
+                          guider_config={"target": "vista_b200.diffusion.TrianglePredictionGuider",
+                                         "params": {"max_scale": 2.5, "num_frames": T}})
+    c, uc = synth.synth_conditioning(7, T, h, w, trajectory=True, context_dim=cfg.context_dim, adm=cfg.adm_in_channels)
+    _, z, _ = synth.synth_latents(7, T, h, w)
+    td = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    zt = torch.from_numpy(z)
+    noises = [torch.from_numpy(synth.normal(20 + i, "rollout.noise", (T, 4, h, w), std=1.0)) for i in range(rounds)]
+    with patched_ops(), torch.no_grad():
+        ours = rollout(lambda nz, cf, m: smp(denoiser, nz, cond=td(c), uc=td(uc), cond_frame=cf, cond_mask=m), zt, noises, T)
+    assert calls["fused"] == rounds, "the reference's closure must reach the fused loop"
+    sdt = to_t(sd)
+    with torch.no_grad():
+        ref = rollout(lambda nz, cf, m: vo.euler_edm_sample(sdt, cfg, nz, td(c), td(uc), cf, m, steps, T,
+                                                            guider="TrianglePredictionGuider", scale=2.5), zt, noises, T)
+    assert ours.shape == ref.shape == (rounds * (T - 3) + 3, 4, h, w)
+    r = rel_l2(ours, ref)
+    assert r < 5e-3, r

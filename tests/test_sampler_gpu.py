@@ -157,3 +157,39 @@ def test_engine_sample_then_decode_vs_oracle():
     print(f"engine: latent rel-L2 {r1:.3e}, decoded frames rel-L2 {r2:.3e} (frames absmean {float(frames_ref.abs().mean()):.3f})")
     assert frames.shape == (T, 3, 2 * h, 2 * w)
     assert r1 < 5e-3 and r2 < 1e-2
+
+
+def test_multi_round_rollout_through_the_reference_closure_vs_oracle():
+    """BASELINE config 4 semantics (sample_utils.py:318-365) on the GPU: two rounds, TrianglePredictionGuider, later
+    rounds conditioned on the last three latents; the sampler gets the reference's own closure around an engine-like
+    object (fused CUDA-graph loop behind it).  Compared with the same loop on the CPU oracle (same body as the
+    emulated-operator test in tests/test_executor_cpu.py)."""
+    from helpers import rollout
+    from oracle import vista_oracle as vo
+    cfg, net, den, _ = build("tiny")
+    _, sd = unet_weights("tiny")
+
+    class Engine:
+        pass
+    model = Engine()
+    model.model, model.denoiser = net, den
+
+    def denoiser(x, sigma, cond, cond_mask):           # sample_utils.py:314-315, verbatim shape
+        return model.denoiser(model.model, x, sigma, cond, cond_mask)
+    T, h, w, steps, rounds = 25, 8, 16, 3, 2
+    smp = make_sampler(steps, "TrianglePredictionGuider")
+    c, uc = synth.synth_conditioning(7, T, h, w, trajectory=True, context_dim=cfg.context_dim, adm=cfg.adm_in_channels)
+    _, z, _ = synth.synth_latents(7, T, h, w)
+    noises = [torch.from_numpy(synth.normal(20 + i, "rollout.noise", (T, 4, h, w), std=1.0)) for i in range(rounds)]
+    ours = rollout(lambda nz, cf, m: smp(denoiser, nz, cond=to_t(c, DEV), uc=to_t(uc, DEV), cond_frame=cf, cond_mask=m),
+                   torch.from_numpy(z).to(DEV), [n.to(DEV) for n in noises], T)
+    torch.cuda.synchronize()
+    sdt = to_t(sd)
+    with torch.no_grad():
+        ref = rollout(lambda nz, cf, m: vo.euler_edm_sample(sdt, cfg, nz, to_t(c), to_t(uc), cf, m, steps, T,
+                                                            guider="TrianglePredictionGuider", scale=2.5),
+                      torch.from_numpy(z), noises, T)
+    r = rel_l2(ours.cpu(), ref)
+    print(f"rollout ({rounds} rounds x {steps} steps): rel-L2 vs oracle {r:.3e}")
+    assert ours.shape == ref.shape == (rounds * (T - 3) + 3, 4, h, w)
+    assert r < 5e-3, r
