@@ -336,3 +336,62 @@ def test_multi_round_rollout_through_the_reference_closure_on_emulated_ops(monke
     assert ours.shape == ref.shape == (rounds * (T - 3) + 3, 4, h, w)
     r = rel_l2(ours, ref)
     assert r < 5e-3, r
+
+
+def test_engine_encode_sample_decode_on_emulated_ops(monkeypatch):
+    """The DiffusionEngine surface end to end on emulated operators, built from configs/inference/vista_b200.yaml with
+    tiny sizes and the (experimental) B200 encoder plugged in: encode_first_stage(images) -> sample() ->
+    decode_first_stage(), each stage against the CPU oracle, plus the reference checkpoint key layout."""
+    import os
+    import yaml
+    from helpers import decoder_weights, unet_weights
+    from oracle import vista_oracle as vo
+    from vista_b200 import fused as fused_mod
+    from vista_b200.diffusion import instantiate_from_config
+    monkeypatch.setattr(fused_mod, "USE_GRAPH", False)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, "configs", "inference", "vista_b200.yaml")))["model"]
+    p = cfg["params"]
+    p["network_config"]["params"].update(model_channels=64, channel_mult=[1, 2], num_res_blocks=1, attention_resolutions=[1, 2])
+    fs = p["first_stage_config"]["params"]
+    fs["decoder_config"]["params"].update(ch=64, ch_mult=[1, 2], num_res_blocks=1)
+    fs["encoder_config"] = {"target": "vista_b200.vae.Encoder",
+                            "params": dict(attn_type="vanilla", double_z=True, z_channels=4, resolution=256, in_channels=3,
+                                           out_ch=3, ch=64, ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[], dropout=0.0)}
+    p["sampler_config"]["params"]["num_steps"] = 3
+    p["sampler_config"]["params"]["device"] = "cpu"
+    p["replace_cond_frames"], p["fixed_cond_frames"] = True, [0]
+    p["en_and_decode_n_samples_a_time"] = 14
+    eng = instantiate_from_config(cfg)
+    ucfg, usd = unet_weights("tiny")
+    dcfg, dsd = decoder_weights("tiny")
+    ecfg = spec.encoder_preset("tiny")
+    esd = synth.synth_state_dict(spec.encoder_param_specs(ecfg), seed=3)
+    sd = {"model.diffusion_model." + k: torch.from_numpy(v) for k, v in usd.items()}
+    sd.update({"first_stage_model.decoder." + k: torch.from_numpy(v) for k, v in dsd.items()})
+    sd.update({"first_stage_model.encoder." + k: torch.from_numpy(v) for k, v in esd.items()})
+    missing, unexpected = eng.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    eng.model._require_cuda = eng.model.diffusion_model._require_cuda = lambda device: None
+    from vista_b200 import vae as vae_mod                      # CPU executors for this test only
+    monkeypatch.setattr(vae_mod.VideoDecoder, "runtime", lambda self, device: self.__dict__.setdefault(
+        "_rt_cpu", vae_mod.DecoderRuntime(self.b200_config, self.state_dict(), "cpu")))
+    monkeypatch.setattr(vae_mod.Encoder, "runtime", lambda self, device: self.__dict__.setdefault(
+        "_rt_cpu", vae_mod.EncoderRuntime(self.b200_config, self.state_dict(), "cpu")))
+    T, h, w = 25, 8, 16
+    images = torch.from_numpy(synth.normal(31, "engine.images", (T, 3, 2 * h, 2 * w), std=0.5))
+    enc_noise = torch.from_numpy(synth.normal(32, "engine.encnoise", (T, 4, h, w), std=1.0))
+    c, uc = synth.synth_conditioning(7, T, h, w, trajectory=True, context_dim=ucfg.context_dim, adm=ucfg.adm_in_channels)
+    noise, _, mask = synth.synth_latents(7, T, h, w)
+    mask[:1] = 1.0
+    td = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    with patched_ops(), torch.no_grad():
+        z = eng.encode_first_stage(images, noise=enc_noise)
+        lat = eng.sample(td(c), cond_frame=z, uc=td(uc), N=T, shape=(4, h, w), noise=torch.from_numpy(noise))
+        frames = eng.decode_first_stage(lat)
+    with torch.no_grad():
+        z_ref = vo.encode_first_stage(to_t(esd), ecfg, images, n_samples=14, noise=enc_noise)
+        lat_ref = vo.euler_edm_sample(to_t(usd), ucfg, torch.from_numpy(noise), td(c), td(uc), z_ref, torch.from_numpy(mask), 3, T)
+        frames_ref = vo.decode_first_stage(to_t(dsd), dcfg, lat_ref)
+    assert rel_l2(z, z_ref) < 5e-3 and rel_l2(lat, lat_ref) < 5e-3 and rel_l2(frames, frames_ref) < 1e-2
+    assert frames.shape == (T, 3, 2 * h, 2 * w)
