@@ -103,6 +103,13 @@ int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const void* k, int64
 int b200v_attention_spatial_v4(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                                void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
+/* Fifth generation (the default for long sequences): persistent kernel, one CTA per SM walking (frame, head, 256-query
+ * block) work items; two 128-query tiles per CTA in ping-pong, one thread per query row, P written back into tensor
+ * memory over the consumed scores (tcgen05.st) and O += P [V | 1] issued with the A operand in TMEM; K / V in 3-deep
+ * TMA rings shared by the two tiles, Q of the next item prefetched into a second buffer. */
+int b200v_attention_spatial_v5(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                               void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
+
 /* Temporal self-attention over the T frames of each pixel (seq len T <= 32, head dim 64).
  * Replaces the batchified xformers call at vwm/modules/attention.py:384-399 reached from
  * vwm/modules/video_attention.py:127 and both "(b t) s c <-> (b s) t c" rearranges (:116,:140):

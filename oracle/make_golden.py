@@ -30,11 +30,20 @@ UNET_CASES = {
 SAMPLER_CASES = {
     "sampler_tiny_cfg": ("tiny", 8, 16, 25, 4, "VanillaCFG", 1),
     "sampler_tiny_triangle": ("tiny", 8, 16, 25, 3, "TrianglePredictionGuider", 3),
+    # BASELINE config 2's step count on the `small` network: error growth over a full 50-step trajectory
+    "sampler_small_cfg50": ("small", 16, 32, 25, 50, "VanillaCFG", 1),
 }
 # name -> (decoder preset, h, w, n latent frames)
 DECODER_CASES = {
     "decoder_tiny": ("tiny", 8, 16, 14),
     "decoder_small": ("small", 8, 16, 14),
+}
+# The measured decoder architecture (vista.yaml: ch = 128, mult 1-2-4-4) on latents of the real magnitude (std 1/0.18215 = 5.5
+# after decode_first_stage's division): name -> (preset, h, w, frames, pixel stride of the stored samples).  The outputs are
+# too large to commit whole: strided samples + the mean of every 8 x 8 pixel block (fp64 -> fp32) of the full output.
+DECODER_BIG_CASES = {
+    "decoder_vista_16x32": ("vista", 16, 32, 14, 2),
+    "decoder_vista_72x128_t5": ("vista", 72, 128, 5, 8),     # full BASELINE spatial size (d = 512, N = 9216 attention)
 }
 DECODE_FS_CASES = {
     "decode_first_stage_tiny": ("tiny", 8, 16, 25),
@@ -94,12 +103,23 @@ def gen_sampler(name):
     c, uc = synth.synth_conditioning(7, T, h, w, trajectory=True, context_dim=cfg.context_dim, adm=cfg.adm_in_channels)
     noise, z, mask = synth.synth_latents(7, T, h, w)
     mask[:n_cond] = 1.0
+    # long trajectories also keep the sampler state entering steps 5 / 10 / 25 (the first half of the CFG-doubled x the
+    # reference hands to the denoiser at that call): error growth along the trajectory can then be checked, not only its end
+    keep = {i: None for i in (5, 10, 25) if i < steps} if steps >= 10 else {}
+    calls = {"i": 0}
+
+    def denoise(x, s, cc, m):
+        if calls["i"] in keep:
+            keep[calls["i"]] = x[: x.shape[0] // 2].clone().numpy()
+        calls["i"] += 1
+        return den(net, x, s, cc, m)
+    t0 = time.time()
     with torch.no_grad():
-        out = smp(lambda x, s, cc, m: den(net, x, s, cc, m), torch.from_numpy(noise.copy()), cond=to_t(c), uc=to_t(uc),
+        out = smp(denoise, torch.from_numpy(noise.copy()), cond=to_t(c), uc=to_t(uc),
                   cond_frame=torch.from_numpy(z), cond_mask=torch.from_numpy(mask))
-    print(f"{name}: absmean {out.abs().mean():.4f}")
+    print(f"{name}: absmean {out.abs().mean():.4f} ({time.time() - t0:.0f}s, {calls['i']} denoiser calls)")
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), sample=out.numpy(),
-                        weight_checksum=synth.state_dict_checksum(sd))
+                        weight_checksum=synth.state_dict_checksum(sd), **{f"state_{i}": v for i, v in keep.items()})
 
 
 def gen_decoder(name):
@@ -114,6 +134,25 @@ def gen_decoder(name):
     print(f"{name}: out {tuple(out.shape)} absmean {out.abs().mean():.4f}")
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), out=out.numpy(),
                         weight_checksum=synth.state_dict_checksum(sd))
+
+
+def gen_decoder_big(name):
+    preset, h, w, n, stride = DECODER_BIG_CASES[name]
+    cfg = spec.decoder_preset(preset)
+    sd = synth.synth_state_dict(spec.decoder_param_specs(cfg), seed=2)
+    dec = ref_loader.build_ref_decoder(cfg)
+    dec.load_state_dict(to_t(sd), strict=True)
+    z = synth.normal(9, "decbig.z", (n, cfg.z_channels, h, w), std=1.0 / 0.18215)
+    t0 = time.time()
+    with torch.no_grad():
+        out = dec(torch.from_numpy(z), timesteps=n)
+    dt = time.time() - t0
+    H, W = out.shape[2], out.shape[3]
+    bm = out.double().reshape(n, out.shape[1], H // 8, 8, W // 8, 8).mean(dim=(3, 5)).float()
+    print(f"{name}: out {tuple(out.shape)} absmean {out.abs().mean():.4f} rms {out.pow(2).mean().sqrt():.4f} ({dt:.0f}s)")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), samples=out[:, :, ::stride, ::stride].contiguous().numpy(),
+                        block_means=bm.numpy(), stride=stride, rms=float(out.pow(2).mean().sqrt()),
+                        weight_checksum=synth.state_dict_checksum(sd), cpu_seconds=dt)
 
 
 def gen_decode_fs(name):
@@ -247,6 +286,8 @@ def main(argv):
             gen_sampler(cname)
         elif cname in DECODER_CASES:
             gen_decoder(cname)
+        elif cname in DECODER_BIG_CASES:
+            gen_decoder_big(cname)
         elif cname in DECODE_FS_CASES:
             gen_decode_fs(cname)
         elif cname in ENCODER_CASES:

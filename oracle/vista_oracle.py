@@ -274,8 +274,10 @@ def guider_scales(guider: str, num_frames: int, scale: float) -> torch.Tensor:
 
 
 def euler_edm_sample(sd, cfg, noise, c, uc, cond_frame, cond_mask, num_steps, num_frames=25,
-                     guider="VanillaCFG", scale=2.5, return_all=False):
-    """sampling.py:91-124 (s_churn = 0 -> gamma = 0) + guiders.py:19-36 (batch [uncond; cond])."""
+                     guider="VanillaCFG", scale=2.5, return_all=False, stop_after=None):
+    """sampling.py:91-124 (s_churn = 0 -> gamma = 0) + guiders.py:19-36 (batch [uncond; cond]).
+    stop_after = k (test aid): leave the num_steps-schedule after k steps and return the state the reference hands to
+    its denoiser at call k (conditioning frames re-imposed, sampling.py:105-106)."""
     sigmas = edm_sigmas(num_steps)
     x = noise.clone() * torch.sqrt(1.0 + sigmas[0] ** 2)          # :36
     scales = guider_scales(guider, num_frames, scale)[:, None, None, None]
@@ -297,6 +299,8 @@ def euler_edm_sample(sd, cfg, noise, c, uc, cond_frame, cond_mask, num_steps, nu
         x = x + d * (nxt - sig)[:, None, None, None]              # sampling.py:85-88
         if return_all:
             traj.append(x.clone())
+        if stop_after is not None and i + 1 == stop_after:
+            break
     if replace:
         x = x * keep + cond_frame * put                           # :122-123
     return (x, traj) if return_all else x

@@ -13,7 +13,8 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 # spatial-attention kernel generations under test; 4 (P in tensor memory) is experimental and opt-in
-ATTN_IMPLS = [1, 2, 3] + ([4] if os.environ.get("VISTA_B200_TEST_ATTN4") == "1" else [])
+ATTN_IMPLS = [int(v) for v in os.environ.get("VISTA_B200_TEST_ATTN_IMPLS", "1,2,3,5").split(",")] \
+    + ([4] if os.environ.get("VISTA_B200_TEST_ATTN4") == "1" else [])
 
 
 @pytest.fixture(scope="module")
@@ -148,7 +149,10 @@ def test_gemm_temporal_conv(ops, nb, T, S, Cc):
 # ------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("impl", ATTN_IMPLS)
 @pytest.mark.parametrize("frames,seq,heads", [(2, 128, 1), (3, 144, 2), (2, 576, 4), (1, 2304, 2), (2, 200, 1), (1, 256, 1),
-                                              (2, 300, 1)])
+                                              (2, 300, 1),
+                                              # more work items than SMs (persistent loop of v5: 200 / 200 items), with and
+                                              # without a skipped second query tile in the last block of a (frame, head)
+                                              (10, 1280, 4), (20, 320, 5)])
 def test_attention_spatial(ops, frames, seq, heads, impl):
     Cc = heads * 64
     qkv = rnd(frames * seq, 3 * Cc, seed=23)

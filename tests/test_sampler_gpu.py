@@ -67,6 +67,32 @@ def test_fused_and_generic_sampler_vs_reference(name, steps, guider, n_cond):
     assert torch.equal(fused[:n_cond], z[:n_cond])          # conditioning frames re-imposed (sampling.py:122-123)
 
 
+def test_50_step_trajectory_vs_reference():
+    """BASELINE config 2's step count on the `small` network at 16 x 32: error growth over the whole trajectory.  The
+    generic loop records the state entering steps 5 / 10 / 25 (what the reference handed to ITS denoiser at those
+    calls, tests/golden/sampler_small_cfg50.npz); the fused (CUDA-graph) loop is held to the final latent."""
+    g = golden("sampler_small_cfg50")
+    cfg, net, den, bden = build("small")
+    c, uc, noise, z, mask = inputs(cfg, 25, 16, 32, 1)
+    smp = make_sampler(50)
+    seen, calls = {}, {"i": 0}
+
+    def denoise(x, s, cc, m):
+        if calls["i"] in (5, 10, 25):
+            seen[calls["i"]] = x[: x.shape[0] // 2].clone()
+        calls["i"] += 1
+        return den(net, x, s, cc, m)
+    generic = smp(denoise, noise.clone(), c, uc=uc, cond_frame=z, cond_mask=mask)
+    fused = smp(bden, noise.clone(), c, uc=uc, cond_frame=z, cond_mask=mask)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["sample"])
+    errs = {i: rel_l2(seen[i].cpu(), torch.from_numpy(g[f"state_{i}"])) for i in (5, 10, 25)}
+    rg, rf = rel_l2(generic.cpu(), ref), rel_l2(fused.cpu(), ref)
+    print("50-step trajectory rel-L2 vs reference: " + ", ".join(f"step {i}: {e:.3e}" for i, e in errs.items())
+          + f", final generic {rg:.3e}, final fused {rf:.3e}")
+    assert max(errs.values()) < 5e-3 and rg < 5e-3 and rf < 5e-3
+
+
 def test_fused_graph_equals_eager(monkeypatch):
     from vista_b200 import fused as F
     cfg, net, den, bden = build("tiny")

@@ -126,13 +126,33 @@ class _RuntimeOwner:
         self._runtime, self._runtime_key, self._cond_cache = None, None, None
 
     @staticmethod
+    def _placement(module: nn.Module):
+        """(device, dtype) of every parameter: what `.cuda()` / `.half()` / `.to()` can change."""
+        return tuple((p.device, p.dtype) for p in module.parameters())
+
+    def _apply_keep_runtime(self, fn, *args, **kwargs):
+        """nn.Module._apply that drops the packed runtime only when a parameter really moved or changed dtype: the
+        reference's do_sample calls `load_model(model.model)` (= an unconditional `.cuda()`, sample_utils.py:34-47)
+        once per call, which must not cost a re-pack of 1.6 B parameters and a graph re-capture."""
+        before = self._placement(self)
+        out = nn.Module._apply(self, fn, *args, **kwargs)
+        if self._placement(self) != before:
+            self._rt_invalidate()
+        return out
+
+    @staticmethod
+    def _weights_version(model: nn.Module) -> int:
+        """Changes whenever a parameter is written in place (load_state_dict copies in place) or replaced."""
+        return hash(tuple((id(p), p._version) for p in model.parameters()))
+
+    @staticmethod
     def _require_cuda(device):
         if not torch.cuda.is_available() or torch.device(device).type != "cuda":
             raise RuntimeError("vista_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
 
     def _rt_get(self, model: nn.Module, num_frames: int, device) -> UNetRuntime:
         self._require_cuda(device)
-        key = (num_frames, str(device), id(model), self.frame_sharded)
+        key = (num_frames, str(device), id(model), self.frame_sharded, self._weights_version(model))
         if self._runtime is None or self._runtime_key != key:
             cfg = _infer_config(model)
             if self.frame_sharded and self._frame_world > 1:
@@ -225,9 +245,8 @@ class VideoUNet(nn.Module, _RuntimeOwner):
         self._rt_init()
         self.register_load_state_dict_post_hook(lambda module, keys: module._rt_invalidate())
 
-    def _apply(self, fn, *args, **kwargs):       # .cuda() / .half() / .to(): re-pack on next forward
-        self._rt_invalidate()
-        return super()._apply(fn, *args, **kwargs)
+    def _apply(self, fn, *args, **kwargs):       # .cuda() / .half() / .to(): re-pack on next forward if anything moved
+        return self._apply_keep_runtime(fn, *args, **kwargs)
 
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: Optional[torch.Tensor] = None,
                 y: Optional[torch.Tensor] = None, time_context: Optional[torch.Tensor] = None,
@@ -246,8 +265,7 @@ class B200Wrapper(nn.Module, _RuntimeOwner):
         self._rt_init()
 
     def _apply(self, fn, *args, **kwargs):
-        self._rt_invalidate()
-        return super()._apply(fn, *args, **kwargs)
+        return self._apply_keep_runtime(fn, *args, **kwargs)
 
     def forward(self, x: torch.Tensor, t: torch.Tensor, c: dict, cond_mask: torch.Tensor, num_frames: int,
                 **kwargs) -> torch.Tensor:

@@ -178,7 +178,7 @@ ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "3"))   # 3: two CTAs/SM, two 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
     l = _lib.load()
     fn = {1: l.b200v_attention_spatial, 2: l.b200v_attention_spatial_v2, 3: l.b200v_attention_spatial_v3,
-          4: l.b200v_attention_spatial_v4}[impl or ATTN_IMPL]     # 4: experimental P-in-TMEM variant (opt-in)
+          4: l.b200v_attention_spatial_v4, 5: l.b200v_attention_spatial_v5}[impl or ATTN_IMPL]
     _count(1)
     _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
                 2.0 * 4 * frames * seq * heads * 64)
@@ -214,9 +214,11 @@ class GNWorkspace:
         self.device = device
         self.partials = torch.empty(1 << 16, dtype=torch.float64, device=device)
         self.counters = torch.zeros(max_stats, dtype=torch.int32, device=device)
+        self._retired = []     # outgrown buffers stay alive: captured CUDA graphs / launch tapes hold their raw pointers
 
     def reserve(self, n_doubles: int):
         if self.partials.numel() < n_doubles:
+            self._retired.append(self.partials)
             self.partials = torch.empty(n_doubles, dtype=torch.float64, device=self.device)
 
 

@@ -294,7 +294,9 @@ class ShardedDecoderRuntime(DecoderRuntime):
         """z_tokens: rows of THIS rank's T frames of the chunk -> (T, 3, 8h, 8w) fp32 frames (time mix included)."""
         cfg = self.cfg
         if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] < max(T, 1):
+            self._bufs.setdefault(("gn.retired",), []).append(getattr(self, "gn_stats", None))   # tapes may still point at it
             self.gn_stats = torch.zeros(self.n_gn, max(T, 1), cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+        if not hasattr(self, "gn_ws"):
             self.gn_ws = ops.GNWorkspace(self.dev)
         up_total = 2 ** (len(cfg.ch_mult) - 1)
         self.gn_ws.reserve(ops.groupnorm_scratch(T, h * w * up_total * up_total, cfg.num_groups))

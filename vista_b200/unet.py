@@ -312,10 +312,15 @@ class UNetRuntime:
         B = c_noise.numel()
         assert B % T == 0 and x_tokens.shape[0] == B * h * w and self.cond["B"] == B
         mc, ed = cfg.model_channels, cfg.time_embed_dim
-        if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] != B:
-            self.gn_stats = torch.zeros(self.n_gn, B, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+        # GroupNorm statistics / scratch are persistent per batch size (never replaced or freed): CUDA graphs and launch
+        # tapes captured for another (B, h, w) keep replaying against the buffers they were captured with
+        key = ("gn.stats", B)
+        if key not in self._bufs:
+            self._bufs[key] = torch.zeros(self.n_gn, B, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+        self.gn_stats = self._bufs[key]
+        if not hasattr(self, "gn_ws"):
             self.gn_ws = ops.GNWorkspace(self.dev)
-            self.gn_ws.reserve(ops.groupnorm_scratch(B, h * w, cfg.num_groups))
+        self.gn_ws.reserve(ops.groupnorm_scratch(B, h * w, cfg.num_groups))
         # --- embeddings (video_model.py:456-471) + all emb_layers of the step in one GEMM
         temb = ops.timestep_embedding(c_noise, self.buf("emb.t", B, mc), mc)
         e_plain = self._mlp_step(temb, self.time_embed, "emb.plain")

@@ -150,7 +150,9 @@ class DecoderRuntime:
         out[out_frame0 + skip_frames : out_frame0 + T] (NCHW fp32, (n,3,8h,8w))."""
         cfg = self.cfg
         if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] < T:
+            self._bufs.setdefault(("gn.retired",), []).append(getattr(self, "gn_stats", None))   # tapes may still point at it
             self.gn_stats = torch.zeros(self.n_gn, T, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+        if not hasattr(self, "gn_ws"):
             self.gn_ws = ops.GNWorkspace(self.dev)
         up_total = 2 ** (len(cfg.ch_mult) - 1)
         self.gn_ws.reserve(ops.groupnorm_scratch(T, h * w * up_total * up_total, cfg.num_groups))
@@ -270,7 +272,9 @@ class EncoderRuntime(DecoderRuntime):
         (mean | logvar columns)."""
         cfg = self.cfg
         if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] < n:
+            self._bufs.setdefault(("gn.retired",), []).append(getattr(self, "gn_stats", None))
             self.gn_stats = torch.zeros(self.n_gn, n, cfg.num_groups, 2, dtype=torch.float32, device=self.dev)
+        if not hasattr(self, "gn_ws"):
             self.gn_ws = ops.GNWorkspace(self.dev)
         self.gn_ws.reserve(ops.groupnorm_scratch(n, h * w, cfg.num_groups))
         x = ops.conv3x3_small_cin(x_tokens, cfg.in_channels, self.conv_in_w, self.conv_in_b,
@@ -338,9 +342,12 @@ class Encoder(nn.Module):
         self._runtime = None
         self.register_load_state_dict_post_hook(lambda module, keys: setattr(module, "_runtime", None))
 
-    def _apply(self, fn, *args, **kwargs):
-        self._runtime = None
-        return super()._apply(fn, *args, **kwargs)
+    def _apply(self, fn, *args, **kwargs):     # keep the packed runtime unless a parameter moved / changed dtype
+        before = tuple((p.device, p.dtype) for p in self.parameters())
+        out = super()._apply(fn, *args, **kwargs)
+        if tuple((p.device, p.dtype) for p in self.parameters()) != before:
+            self._runtime = None
+        return out
 
     def runtime(self, device) -> EncoderRuntime:
         if torch.device(device).type != "cuda":
@@ -447,9 +454,12 @@ class VideoDecoder(nn.Module):
         self._runtime = None
         self.register_load_state_dict_post_hook(lambda module, keys: setattr(module, "_runtime", None))
 
-    def _apply(self, fn, *args, **kwargs):
-        self._runtime = None
-        return super()._apply(fn, *args, **kwargs)
+    def _apply(self, fn, *args, **kwargs):     # keep the packed runtime unless a parameter moved / changed dtype
+        before = tuple((p.device, p.dtype) for p in self.parameters())
+        out = super()._apply(fn, *args, **kwargs)
+        if tuple((p.device, p.dtype) for p in self.parameters()) != before:
+            self._runtime = None
+        return out
 
     def runtime(self, device) -> DecoderRuntime:
         if torch.device(device).type != "cuda":
