@@ -96,8 +96,8 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* v_full = k_empty + kNS5;
   uint64_t* v_empty = v_full + kNS5;
   uint64_t* s_full = v_empty + kNS5;                      // [2] per tile
-  uint64_t* p_full = s_full + 2;                          // [2]
-  uint64_t* o_full = p_full + 2;                          // [2]
+  uint64_t* p_full = s_full + 2;                          // [2 tiles][4 chunks of 32 keys]
+  uint64_t* o_full = p_full + 8;                          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
   uint8_t* sQ = smem + 1024;                   // 2 buffers x 2 tiles
   uint8_t* sK = sQ + 4 * kT5Bytes;             // kNS5 stages
@@ -112,9 +112,9 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
       mbar_init(&o_full[i], 1);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&p_full[i], 128);
     for (int i = 0; i < kNS5; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -205,32 +205,76 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_after();
         for (int t = 0; t < nt; ++t) issue_s(t, kv);
         umma_commit(&k_empty[kv % kNS5]);
-        for (int j = 0; j < n_kv; ++j) {
-          const uint32_t cur = kv + j;
-          const int st = cur % kNS5;
-          const bool more = j + 1 < n_kv;
-          for (int t = 0; t < nt; ++t) {
-            mbar_wait(&p_full[t], g[t] & 1, 56);
-            if (t == 0) mbar_wait(&v_full[st], (cur / kNS5) & 1, 57);
+        // Event-driven issue: per tile the next action is either "PV of the next 32-key chunk of block jt" (as soon as
+        // the softmax warpgroup has stored that chunk of P: the PV MMAs of a block overlap the rest of its softmax) or
+        // "S of block jt" (right behind the last PV chunk of block jt - 1: the aliased P columns are consumed in
+        // order).  Nothing blocks: a tile that is not ready is skipped, so the two tiles never gate each other.
+        int jt[2] = {0, 0}, ch[2] = {0, 0};
+        bool s_pending[2] = {false, false};
+        int left = nt;
+        int vdone[kNS5], kdone[kNS5];
+#pragma unroll
+        for (int i = 0; i < kNS5; ++i) vdone[i] = kdone[i] = 0;
+        uint32_t spins = 0;
+        long long t_idle = 0;
+        while (left > 0) {
+          bool progress = false;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (t >= nt || jt[t] >= n_kv) continue;
+            const uint32_t cur = kv + jt[t];
+            const int st = cur % kNS5;
+            if (s_pending[t]) {
+              if (!mbar_try_wait(&k_full[st], (cur / kNS5) & 1)) continue;
+              tc_fence_after();
+              issue_s(t, cur);
+              s_pending[t] = false;
+              if (++kdone[st] == nt) {
+                umma_commit(&k_empty[st]);
+                kdone[st] = 0;
+              }
+              progress = true;
+              continue;
+            }
+            if (!mbar_try_wait(&p_full[t * 4 + ch[t]], g[t] & 1)) continue;
+            if (ch[t] == 0 && !mbar_try_wait(&v_full[st], (cur / kNS5) & 1)) continue;
             tc_fence_after();
             const uint32_t v_base = smem_u32(sV + st * kT5Bytes);
             const uint32_t lbo = ones_base - v_base;     // second N atom (columns 64..79) = the ones atom
 #pragma unroll
-            for (int k = 0; k < 8; ++k)                  // keys 16 k .. 16 k + 15: 8 packed columns of P
+            for (int kk = 0; kk < 2; ++kk) {             // keys 16 k .. 16 k + 15: 8 packed columns of P
+              const int k = 2 * ch[t] + kk;
               umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
-                          make_desc_sw128(v_base + k * 2048, lbo, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
-            ++g[t];
-            if (t == nt - 1) umma_commit(&v_empty[st]);  // both tiles are done with V_j
-            if (!more) {
-              umma_commit(&o_full[t]);
-              ++items_t[t];
-            } else {
-              if (t == 0) {
-                mbar_wait(&k_full[(cur + 1) % kNS5], ((cur + 1) / kNS5) & 1, 58);
-                tc_fence_after();
+                          make_desc_sw128(v_base + k * 2048, lbo, 1024), idesc_o, (jt[t] | k) != 0 ? 1u : 0u);
+            }
+            progress = true;
+            if (++ch[t] == 4) {
+              ch[t] = 0;
+              ++g[t];
+              if (++vdone[st] == nt) {                   // both tiles are done with V of this block
+                umma_commit(&v_empty[st]);
+                vdone[st] = 0;
               }
-              issue_s(t, cur + 1);
-              if (t == nt - 1) umma_commit(&k_empty[(cur + 1) % kNS5]);
+              if (jt[t] + 1 == n_kv) {
+                umma_commit(&o_full[t]);
+                ++items_t[t];
+                jt[t] = n_kv;
+                --left;
+              } else {
+                ++jt[t];
+                s_pending[t] = true;
+              }
+            }
+          }
+          if (progress) {
+            spins = 0;
+            t_idle = 0;
+          } else if ((++spins & 4095u) == 0u) {          // bounded: a pipeline bug ends in a trap, not a hung box
+            const long long now = clock64();
+            if (t_idle == 0) t_idle = now;
+            if (now - t_idle > VB_WAIT_TIMEOUT_CYCLES) {
+              printf("vista_b200: attn5 issuer stalled block=%d jt=(%d,%d) ch=(%d,%d)\n", blockIdx.x, jt[0], jt[1], ch[0], ch[1]);
+              __trap();
             }
           }
         }
@@ -310,10 +354,10 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
           }
           tmem5_st16(tS + c * 16, pw);
+          tmem5_st_wait();                 // (also covers the O rescale stores above)
+          tc_fence_before();
+          mbar_arrive(&p_full[t * 4 + c]);
         }
-        tmem5_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[t]);
       }
       // epilogue: O / rowsum
       mbar_wait(&o_full[t], items_done & 1, 60);

@@ -19,8 +19,15 @@ class FirstStage(nn.Module):
     """Holds the decoder under the reference's key prefix ``first_stage_model.decoder.*``
     (AutoencodingEngine.decode, vwm/models/autoencoder.py:206-208)."""
 
-    def __init__(self, decoder_config: Dict, encoder_config: Optional[Dict] = None, **ignored):
+    def __init__(self, decoder_config: Dict, encoder_config: Optional[Dict] = None, **reference_only):
         super().__init__()
+        # AutoencodingEngine keywords (vwm/models/autoencoder.py:106-125) without a meaning at inference are accepted
+        known = {"loss_config", "regularizer_config", "optimizer_config", "lr_g_factor", "trainable_ae_params",
+                 "ae_optimizer_args", "trainable_disc_params", "disc_optimizer_args", "disc_start_iter", "diff_boost_factor",
+                 "ckpt_engine", "ckpt_path", "additional_decode_keys", "ema_decay", "monitor", "input_key"}
+        unknown = sorted(set(reference_only) - known)
+        if unknown:
+            raise TypeError(f"vista_b200.engine.FirstStage: unexpected keyword(s) {unknown}")
         self.decoder = instantiate_from_config(decoder_config)
         # optional: the experimental B200 encoder (SURVEY.md §8f rank 1, vista_b200.vae.Encoder), keys
         # ``first_stage_model.encoder.*`` as in the reference checkpoint
@@ -42,13 +49,25 @@ class DiffusionEngine(nn.Module):
                  conditioner_config=None, sampler_config: Optional[Dict] = None, scale_factor: float = 1.0,
                  disable_first_stage_autocast: bool = False, en_and_decode_n_samples_a_time: Optional[int] = None,
                  num_frames: int = 25, network_wrapper: Optional[str] = None, replace_cond_frames: bool = False,
-                 fixed_cond_frames: Optional[List[int]] = None, input_key: str = "img_seq", **ignored):
+                 fixed_cond_frames: Optional[List[int]] = None, input_key: str = "img_seq", **reference_only):
         super().__init__()
+        # keywords of the reference constructor (vwm/models/diffusion.py:20-46) that only matter for training / logging
+        # are accepted and ignored; anything else is a mistyped YAML key and must not be dropped silently
+        known = {"optimizer_config", "scheduler_config", "loss_fn_config", "ckpt_path", "use_ema", "ema_decay_rate",
+                 "log_keys", "no_cond_log", "compile_model", "slow_spatial_layers", "train_peft_adapters"}
+        unknown = sorted(set(reference_only) - known)
+        if unknown:
+            raise TypeError(f"vista_b200.engine.DiffusionEngine: unexpected keyword(s) {unknown}")
+        if reference_only.get("use_ema") or reference_only.get("ckpt_path"):
+            raise NotImplementedError("use_ema / ckpt_path are training-side options; load weights with load_state_dict")
         model = instantiate_from_config(network_config)
         wrapper = get_obj_from_str(network_wrapper) if network_wrapper else B200Wrapper
         self.model = wrapper(model, compile_model=False)
         self.denoiser = instantiate_from_config(denoiser_config)
         self.sampler = instantiate_from_config(sampler_config) if sampler_config is not None else None
+        # The conditioner (CLIP / VAE-encoder / sinusoids, encoders/modules.py) is outside the hot path: a user-supplied
+        # one is hosted as is (do_sample calls model.conditioner.get_unconditional_conditioning), none is built here.
+        self._conditioner = instantiate_from_config(conditioner_config) if conditioner_config is not None else None
         if first_stage_config is not None:
             params = first_stage_config.get("params", first_stage_config)
             self.first_stage_model = FirstStage(params["decoder_config"], params.get("encoder_config")
@@ -70,7 +89,10 @@ class DiffusionEngine(nn.Module):
 
     @property
     def conditioner(self):
-        raise NotImplementedError("the conditioner (CLIP / VAE-encoder / sinusoids) is outside the hot path; pass c / uc dicts")
+        if self._conditioner is None:
+            raise NotImplementedError("no conditioner_config given: the conditioner (CLIP / VAE-encoder / sinusoids) is "
+                                      "outside the hot path; pass c / uc dicts, or give a conditioner_config to host")
+        return self._conditioner
 
     @contextlib.contextmanager
     def ema_scope(self, context=None):          # no-op at inference (diffusion.py:241-255, use_ema False)
@@ -84,7 +106,8 @@ class DiffusionEngine(nn.Module):
         if getattr(self.model, "frame_sharded", False):     # one clip on several ranks: deal the chunks out as well
             from .vae import decode_first_stage_parallel
             return decode_first_stage_parallel(dec.runtime(z.device), z, self.scale_factor,
-                                               self.en_and_decode_n_samples_a_time, overlap)
+                                               self.en_and_decode_n_samples_a_time, overlap,
+                                               group=getattr(self.model, "world_group", None))
         return _decode_first_stage(dec.runtime(z.device), z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap)
 
     @torch.no_grad()

@@ -71,7 +71,7 @@ class _LoopState:
         if self.split is not None:                # guidance needs both halves of the frames this rank owns
             import torch.distributed as dist
             full, pg = self.net_full, self.split[1]
-            _lib.tape_host(lambda src=net_out: dist.all_gather_into_tensor(full, src, group=pg))   # bind now: net_out is rebound below
+            _lib.tape_host(lambda src=net_out: dist.all_gather_into_tensor(full, src, group=pg), "cfg pair all_gather")   # bind now: net_out is rebound below
             net_out = full
         ops.sampler_update(self.x, net_out, self.cond_frame, self.mask, self.scales, self.sigmas, self.step,
                            num_steps, self.N, self.h, self.w)

@@ -187,10 +187,18 @@ def taping() -> bool:
     return _tape is not None
 
 
-def tape_host(fn):
+HOST_PROFILE = None     # (begin(family, detail, flops, bytes), end()): brackets host-side operations with CUDA events (bench.py)
+
+
+def tape_host(fn, detail: str = "host"):
     """Run a host-side operation now and, while a tape is being recorded, put it on the tape."""
     if _tape is not None:
         _tape.append((fn, ()))
+    if HOST_PROFILE is not None:
+        HOST_PROFILE[0]("nccl+host", detail, 0.0, 0.0)
+        r = fn()
+        HOST_PROFILE[1]()
+        return r
     return fn()
 
 

@@ -105,6 +105,7 @@ class _RuntimeOwner:
         if cfg_split is None:
             cfg_split = world % 2 == 0 and os.environ.get("VISTA_B200_CFG_SPLIT", "1") != "0"
         self.frame_sharded = True
+        self.world_group = group          # the group the clip is spread over (engine.decode_first_stage deals chunks over it)
         self.cfg_half, self.pair_group = None, None
         if cfg_split:
             assert world % 2 == 0, "cfg_split needs an even number of ranks"

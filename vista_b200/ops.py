@@ -260,9 +260,12 @@ def groupnorm_sums(x, frames: int, tokens_per_frame: int, Cc: int, sums: torch.T
         ws = _default_ws.setdefault(x.device, GNWorkspace(x.device))
     ws.reserve(groupnorm_scratch(frames, tokens_per_frame, groups))
     _count(1)
+    _prof_begin("groupnorm", f"sums tokens={frames * tokens_per_frame} C={Cc} fps={frames_per_stat}", 0.0,
+                2.0 * frames * tokens_per_frame * Cc)
     _lib.check(l.b200v_groupnorm_sums(x.data_ptr(), x.stride(0), frames, tokens_per_frame, Cc, groups, frames_per_stat,
                                       ws.partials.data_ptr(), ws.counters.data_ptr(), sums.data_ptr(), _stream()),
                "b200v_groupnorm_sums")
+    _prof_end()
     return sums
 
 
@@ -272,20 +275,26 @@ def groupnorm_finalize_apply(x, y, frames: int, tokens_per_frame: int, gamma, be
     l = _lib.load()
     Cc = gamma.numel()
     _count(2)
+    _prof_begin("groupnorm", f"finalize+apply tokens={frames * tokens_per_frame} C={Cc} fps={frames_per_stat}", 0.0,
+                2.0 * 2 * frames * tokens_per_frame * Cc)
     _lib.check(l.b200v_groupnorm_finalize(sums.data_ptr(), sums.numel() // 2, float(count), eps, stats.data_ptr(), _stream()),
                "b200v_groupnorm_finalize")
     _lib.check(l.b200v_groupnorm_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), frames, tokens_per_frame, Cc,
                                        groups, frames_per_stat, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                        int(silu), _stream()), "b200v_groupnorm_apply")
+    _prof_end()
     return y
 
 
 def attention_temporal_sharded(q, k, v, out, nb: int, Tq: int, T: int, S: int, heads: int, kv_frame_tok: torch.Tensor):
     _count(1)
+    _prof_begin("attn_temporal", f"sharded nb={nb} Tq={Tq} T={T} S={S} heads={heads}", 4.0 * 64 * heads * nb * S * Tq * T,
+                2.0 * (2 * nb * Tq + 2 * nb * T) * S * heads * 64)
     _lib.check(_lib.load().b200v_attention_temporal_sharded(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
                                                             v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
                                                             nb, Tq, T, S, heads, kv_frame_tok.data_ptr(), _stream()),
                "b200v_attention_temporal_sharded")
+    _prof_end()
     return out
 
 

@@ -116,7 +116,7 @@ class ShardedUNetRuntime(UNetRuntime):
         Cc = norm[0].numel()
         sums = self.buf(f"gn.sums{nb}", nb * self.cfg.num_groups, 2, torch.float64)
         ops.groupnorm_sums(x, B, hw, Cc, sums, fps, groups=self.cfg.num_groups, ws=self.gn_ws)
-        _lib.tape_host(lambda: dist.all_reduce(sums, group=self.group))
+        _lib.tape_host(lambda: dist.all_reduce(sums, group=self.group), "gn-sum all_reduce")
         self.comm_bytes += sums.numel() * 8
         count = float(Cc // self.cfg.num_groups) * hw * self.T_full
         return ops.groupnorm_finalize_apply(x, y, B, hw, norm[0], norm[1], eps, silu, sums, count,
@@ -145,10 +145,10 @@ class ShardedUNetRuntime(UNetRuntime):
                             first=(send_first.view(nb, hw, Cc), av[:, 0], send_first, recv_prev),
                             last=(send_last.view(nb, hw, Cc), av[:, T - 1], send_last, recv_next))
         start_halo, wait_halo = halo.start, halo.wait
-        _lib.tape_host(start_halo)
+        _lib.tape_host(start_halo, "halo copy + isend/irecv")
         self.comm_bytes += 2 * nb * hw * Cc * 2 * ((self.prev is not None) + (self.next is not None))
         self.gemm(a, lin, out, taps=ops.TAPS_T3, geom=(hw, T, nb), **epi)
-        _lib.tape_host(wait_halo)
+        _lib.tape_host(wait_halo, "halo wait")
         s_acc = epi.get("s_acc", 1.0)
         w0, w2 = self._tap_weights(lin)
         ov = out.as_strided((nb, T, hw, out.shape[1]), (T * hw * out.stride(0), hw * out.stride(0), out.stride(0), 1))
@@ -184,8 +184,8 @@ class ShardedUNetRuntime(UNetRuntime):
         kv = qkv.as_strided((nb, T, hw, 2 * Cc), (T * hw * qkv.stride(0), hw * qkv.stride(0), qkv.stride(0), 1),
                             qkv.storage_offset() + Cc)
         dst = send.view(nb, Tp, hw, 2 * Cc)[:, :T]
-        _lib.tape_host(lambda: dst.copy_(kv))
-        _lib.tape_host(lambda: dist.all_gather_into_tensor(recv, send, group=self.group))
+        _lib.tape_host(lambda: dst.copy_(kv), "kv staging copy")
+        _lib.tape_host(lambda: dist.all_gather_into_tensor(recv, send, group=self.group), f"kv all_gather C={Cc} hw={hw}")
         self.comm_bytes += recv.numel() * 2
         tab = self._frame_table(nb, hw)
         return ops.attention_temporal_sharded(qkv[:, :Cc], recv[:, :Cc], recv[:, Cc:], o, nb, T, self.T_full, hw, heads, tab)
