@@ -74,9 +74,26 @@ typedef struct b200v_gemm_desc {
   int64_t ld_res2;
   float s_res2;
   float s_acc;
+  /* Optional: GroupNorm statistics of the output, fused into the epilogue (util.py:214-216 reads its input once more in
+   * the reference; here the producer already has the values in registers).  stats != NULL: fp32 column partials — sum and
+   * sum of squares of the stored values over each (128-token tile, 32-row quarter) — are written to
+   * stats[((tile * 4 + quarter) * stats_ld + stats_col0 + n) * 2 + {0, 1}] for every output column n; b200v_groupnorm_
+   * from_partials turns them into (mean, rstd).  Needs fp16 output, act 0, at most one residual, no rowvec with a
+   * residual, and token tiles of 128 consecutive tokens (a_mode 0, or boxes of whole image rows / row segments). */
+  float* stats;
+  int64_t stats_ld;
+  int32_t stats_col0;
 } b200v_gemm_desc;
 
 int b200v_gemm(const b200v_gemm_desc* d, void* stream);
+
+/* (mean, rstd) per (statistic, group) from the column partials b200v_gemm wrote (fixed summation order, fp64):
+ * statistic s covers frames [s * frames_per_stat, (s + 1) * frames_per_stat), each of tokens_per_frame tokens
+ * (a multiple of 128); mean_rstd [n_stats, groups, 2] fp32.  raw_sums (optional, [n_stats, groups, 2] fp64) receives
+ * (sum, sum of squares) instead — the frame-sharded GroupNorm all-reduces those before finalising. */
+int b200v_groupnorm_from_partials(const float* partials, int64_t stats_ld, int32_t n_stats, int32_t frames_per_stat,
+                                  int32_t tokens_per_frame, int32_t C, int32_t groups, float eps, float* mean_rstd,
+                                  double* raw_sums, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Spatial self-attention, head dim 64, non-causal:  softmax(Q K^T / 8) V  per (frame, head).

@@ -14,7 +14,7 @@ def _f(t):
 
 
 def gemm(a, w, out, *, taps=((0, 0),), geom=None, bias=None, rowvec=None, rv_div=1, rv_mod=1, res1=None, s_res1=1.0,
-         res2=None, s_res2=1.0, s_acc=1.0, act=0, tile_n=None, cin=None):
+         res2=None, s_res2=1.0, s_acc=1.0, act=0, tile_n=None, cin=None, stats=None):
     tokens = a.shape[0]
     N, K = w.shape
     ntaps = len(taps)
@@ -55,6 +55,11 @@ def gemm(a, w, out, *, taps=((0, 0),), geom=None, bias=None, rowvec=None, rv_div
         acc = acc + s_res2 * _f(res2)
     n_out = out.shape[1]
     out.copy_(acc[:, :n_out].to(out.dtype))
+    if stats is not None:              # column partials per (128-token tile, 32-row quarter) of the fp32 values, like the kernel
+        pad = (-tokens) % 128
+        v = F.pad(acc[:, :n_out], (0, 0, 0, pad)).reshape(-1, 32, n_out)
+        stats[: v.shape[0], :n_out, 0] = v.sum(dim=1)
+        stats[: v.shape[0], :n_out, 1] = (v * v).sum(dim=1)
     return out
 
 
@@ -76,6 +81,33 @@ def groupnorm(x, y, frames, tokens_per_frame, gamma, beta, eps, silu, stats=None
     mean = xs.mean(dim=(1, 3), keepdim=True)
     var = xs.var(dim=(1, 3), unbiased=False, keepdim=True)
     o = ((xs - mean) * torch.rsqrt(var + eps)).reshape(-1, C) * _f(gamma) + _f(beta)
+    if silu:
+        o = F.silu(o)
+    y.copy_(o.to(y.dtype))
+    return y
+
+
+def groupnorm_from_partials(partials, frames, tokens_per_frame, Cc, eps, stats, frames_per_stat=1, groups=32, raw_sums=None):
+    n_stat = frames // frames_per_stat
+    rows = frames_per_stat * (tokens_per_frame // 128) * 4
+    p = partials[: n_stat * rows, :Cc].double().reshape(n_stat, rows, groups, Cc // groups, 2).sum(dim=(1, 3))
+    if raw_sums is not None:
+        raw_sums.copy_(p.reshape(raw_sums.shape))
+        return stats
+    count = float(Cc // groups) * tokens_per_frame * frames_per_stat
+    mean = p[..., 0] / count
+    var = (p[..., 1] / count - mean * mean).clamp_min(0.0)
+    stats[..., 0] = mean.float()
+    stats[..., 1] = torch.rsqrt(var + eps).float()
+    return stats
+
+
+def groupnorm_apply(x, y, frames, tokens_per_frame, gamma, beta, silu, stats, frames_per_stat=1, groups=32):
+    C = gamma.numel()
+    n_stat = frames // frames_per_stat
+    xs = _f(x[:, :C]).reshape(n_stat, frames_per_stat * tokens_per_frame, groups, C // groups)
+    o = (xs - stats[..., 0][:, None, :, None]) * stats[..., 1][:, None, :, None]
+    o = o.reshape(-1, C) * _f(gamma) + _f(beta)
     if silu:
         o = F.silu(o)
     y.copy_(o.to(y.dtype))
@@ -258,7 +290,7 @@ def sampler_update(x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_s
 
 _PATCHED = ["gemm", "GNWorkspace", "groupnorm_scratch", "groupnorm", "conv3x3_small_cin", "im2col_s2_asym", "upsample2x",
             "softmax_rows", "nchw_to_tokens", "tokens_to_nchw", "time_mix_small", "groupnorm_sums",
-            "groupnorm_finalize_apply", "layernorm", "attention_spatial", "attention_temporal",
+            "groupnorm_finalize_apply", "groupnorm_from_partials", "groupnorm_apply", "layernorm", "attention_spatial", "attention_temporal",
             "attention_temporal_sharded", "timestep_embedding", "blend_emb", "im2col_s2", "sampler_prepare",
             "sampler_update"]
 _NOT_TAPED = {"GNWorkspace", "groupnorm_scratch"}

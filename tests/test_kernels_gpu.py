@@ -115,6 +115,52 @@ def test_gemm_conv3x3(ops, NB, H, W, Cin, Cout):
     check(out.reshape(NB, H, W, Cout), ref.permute(0, 2, 3, 1), name="conv3x3")
 
 
+@pytest.mark.parametrize("kind,NB,H,W,Cin,Cout,fps", [("conv_rv", 4, 8, 128, 64, 320, 1), ("conv_res", 4, 36, 64, 128, 640, 1),
+                                                      ("lin_res", 3, 4, 128, 320, 320, 1), ("tconv_res", 2, 1, 256, 128, 128, 5),
+                                                      ("conv_plain", 2, 16, 256, 64, 128, 2)])
+def test_gemm_fused_groupnorm_statistics(ops, kind, NB, H, W, Cin, Cout, fps):
+    """The STATS epilogue: column partials of the stored output -> b200v_groupnorm_from_partials must give the (mean, rstd)
+    torch computes on the same output tensor, for every epilogue variant that has a fused-statistics instantiation,
+    per-frame and clip-wide (frames_per_stat) statistics, and a partial matrix shared by two producers (column slices)."""
+    tokens = NB * H * W
+    frames = NB if kind != "tconv_res" else NB * fps
+    tpf = tokens // frames if kind != "tconv_res" else W
+    x = rnd(tokens if kind != "tconv_res" else frames * tpf, Cin, seed=61)
+    tokens = x.shape[0]
+    bias = rnd(Cout, seed=63, dtype=torch.float32)
+    res = rnd(tokens, Cout, seed=64)
+    out = torch.empty(tokens, 2 * Cout, dtype=torch.float16, device=dev())[:, Cout:]     # a column slice (skip-concat)
+    part_full = torch.zeros(tokens // 128 * 4, 2 * Cout, 2, dtype=torch.float32, device=dev())
+    part = part_full[:, Cout:]
+    if kind in ("conv_rv", "conv_res", "conv_plain"):
+        w2 = rnd(Cout, 9 * Cin, seed=62, scale=(9 * Cin) ** -0.5)
+        kw = dict(taps=ops.TAPS_3X3, geom=(W, H, NB))
+        if kind == "conv_rv":
+            kw.update(rowvec=rnd(NB, Cout, seed=65, dtype=torch.float32), rv_div=H * W, rv_mod=NB)
+        elif kind == "conv_res":
+            kw.update(res1=res)
+    elif kind == "lin_res":
+        w2 = rnd(Cout, Cin, seed=62, scale=Cin ** -0.5)
+        kw = dict(res1=res)
+    else:
+        w2 = rnd(Cout, 3 * Cin, seed=62, scale=(3 * Cin) ** -0.5)
+        kw = dict(taps=ops.TAPS_T3, geom=(tpf, fps, NB), res1=res, s_acc=0.4)
+    ops.gemm(x, w2, out, bias=bias, stats=part, **kw)
+    ref_out = torch.empty(tokens, Cout, dtype=torch.float16, device=dev())
+    ops.gemm(x, w2, ref_out, bias=bias, **kw)                                          # same launch without statistics
+    st = torch.zeros(frames // fps, 32, 2, dtype=torch.float32, device=dev())
+    ops.groupnorm_from_partials(part, frames, tpf, Cout, 1e-5, st, frames_per_stat=fps)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out)
+    o = out.float().reshape(frames // fps, fps * tpf, 32, Cout // 32)
+    mean = o.mean(dim=(1, 3))
+    rstd = torch.rsqrt(o.var(dim=(1, 3), unbiased=False) + 1e-5)
+    # the partials hold the fp32 values BEFORE the fp16 rounding of the store: agreement to fp16-rounding noise / sqrt(n)
+    assert float((st[..., 0] - mean).abs().max()) < 2e-4 * float(o.abs().max())
+    assert float((st[..., 1] / rstd - 1).abs().max()) < 2e-4
+    assert float(part_full[:, :Cout].abs().max()) == 0.0                                # the other producer's columns untouched
+
+
 def test_gemm_conv3x3_thin_output_f32(ops):
     """out[2] / decoder conv_out path: Cout padded to 8, fp32 output, tile_n 32."""
     NB, H, W, Cin = 2, 9, 16, 320

@@ -61,6 +61,14 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         assert torch.equal(serial, par), "parallel decode differs from the serial decode"
         assert rel_l2(par, torch.from_numpy(golden("decode_first_stage_tiny")["out"])) < 5e-3
+        # frame-sharded decode (every chunk's frames over all ranks: temporal GN all-reduce, (3,1,1) halos, time-mix halos):
+        # same result up to the re-association of the GroupNorm sums; every rank ends with the whole clip
+        from vista_b200.sharded import ShardedDecoderRuntime, decode_first_stage_sharded
+        srt = ShardedDecoderRuntime(dcfg, to_t(dsd), dev)
+        shd = decode_first_stage_sharded(srt, zz).cpu()
+        torch.cuda.synchronize()
+        r_sh = rel_l2(shd, serial)
+        assert r_sh < 1e-3, f"frame-sharded decode vs serial decode: {r_sh:.3e}"
         q.put((rank, res["single"].numpy(), res["frames"].numpy(), res["split"].numpy()))
     finally:
         dist.destroy_process_group()
@@ -104,3 +112,10 @@ def test_four_gpu_sharded_sample_matches_single_gpu():
     if torch.cuda.device_count() < 4:
         pytest.skip("needs 4 GPUs")
     _run_world(4)
+
+
+def test_eight_gpu_sharded_sample_matches_single_gpu():
+    """BASELINE config 5's layout: CFG halves x 4 frame shards (7, 6, 6, 6 frames) and frames-only over 8 ranks."""
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    _run_world(8)

@@ -42,7 +42,7 @@ if "conv1280" in which:
 if "attn" in which:
     qkv = torch.randn(M, 3 * C, device=dev).half()
     o = torch.empty(M, C, dtype=torch.float16, device=dev)
-    for impl in (2, 3):
+    for impl in (5,):
         for _ in range(2):
             ops.attention_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, 50, 9216, 5, impl=impl)
 if "tattn" in which:
@@ -53,9 +53,12 @@ if "tattn" in which:
 if "gn" in which:
     g, bt = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     y = torch.empty_like(x)
+    st = torch.zeros(50, 32, 2, device=dev)
+    st[..., 1] = 1.0
     for fps in (1, 25):
         for _ in range(2):
             ops.groupnorm(x, y, 50, 9216, g, bt, 1e-5, True, frames_per_stat=fps)
+            ops.groupnorm_apply(x, y, 50, 9216, g, bt, True, st[: 50 // fps], frames_per_stat=fps)
 if "ln" in which:
     g, bt = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     y = torch.empty_like(x)

@@ -2,7 +2,7 @@
 //   warps 0-3 : softmax warpgroup of tile A (thread = query row = TMEM lane)
 //   warps 4-7 : softmax warpgroup of tile B
 //   warp 8    : TMA producer (Q of the next work item into the other Q buffer; K / V blocks of 128 keys, NS-deep rings)
-//   warp 9    : TMEM owner + single-thread tcgen05.mma issuer
+//   warps 9, 10 : one tcgen05.mma issuing thread per tile (warp 9 also owns the TMEM allocation)
 // One CTA per SM walks work items (frame, head, 256-query block) round robin; the TMA rings, the TMEM allocation and
 // the constant "ones" operand atom live across items, so the prologue of an item (Q load, first K block) hides behind
 // the tail of the previous one.
@@ -44,6 +44,8 @@ struct Attn5Params {
   long long ld_o;
   void* out;
   float scale_log2;
+  int pingpong;             // 1: the two softmax warpgroups take turns on the exponential phase (MUFU at full rate each)
+  int chunked;              // 1: P is published per 32-key chunk (PV overlaps the softmax of the same block); 0: per block
 };
 
 __device__ __forceinline__ void tmem5_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -83,7 +85,7 @@ __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
 }
 
 template <int EXP>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(352, 1)
 attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Attn5Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -110,16 +112,16 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
+      mbar_init(&q_empty[i], 2);          // one tcgen05.commit per tile issuer
       mbar_init(&s_full[i], 1);
       mbar_init(&o_full[i], 1);
     }
     for (int i = 0; i < 8; ++i) mbar_init(&p_full[i], 128);
     for (int i = 0; i < kNS5; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     fence_barrier_init();
   }
@@ -177,21 +179,25 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
     }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 9 || warp == 10) {
+    // ------------------------------------------------------------ MMA issuers: one thread per tile
+    // Each tile has its own issuing thread (warp 9: tile A, warp 10: tile B): plain blocking waits, no polling, and the
+    // two tiles never gate each other.  Per block: PV of the 32-key chunks as the softmax warpgroup publishes them
+    // (the PV MMAs of a block overlap the rest of its softmax), then S of the next block right behind (the aliased P
+    // columns are consumed in order by the tensor pipe).  The K / V / Q "empty" barriers count one tcgen05.commit
+    // per tile; the issuer of a skipped tile B makes its arrivals without work, in step with the rings.
     if (lane == 0) {
+      const int t = warp - 9;
       const uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0, 0);
       const uint32_t idesc_o = make_idesc_f16(128, 80, 0, 0, 1);   // B = [V | ones] MN-major, N = 64 + 16
       const uint32_t ones_base = smem_u32(sOnes);
-      uint32_t kq = 0, kv = 0;
-      uint32_t g[2] = {0, 0};          // blocks issued per tile (phases of s_full / p_full)
-      uint32_t items_t[2] = {0, 0};    // items finished per tile (phase of o_full)
+      uint32_t kq = 0, kv = 0, g = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++kq) {
         int frame, head, q0;
         decode(item, frame, head, q0);
-        const int nt = (q0 + kT5 < p.seq) ? 2 : 1;       // tile B entirely beyond the sequence: skipped
+        const bool on = t == 0 || (q0 + kT5 < p.seq);    // tile B entirely beyond the sequence: no work
         const int qb = kq & 1;
-        auto issue_s = [&](int t, uint32_t kvi) {
+        auto issue_s = [&](uint32_t kvi) {
           const uint32_t q_base = smem_u32(sQ + (2 * qb + t) * kT5Bytes);
           const uint32_t k_base = smem_u32(sK + (kvi % kNS5) * kT5Bytes);
 #pragma unroll
@@ -203,85 +209,42 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&q_full[qb], (kq >> 1) & 1, 54);
         mbar_wait(&k_full[kv % kNS5], (kv / kNS5) & 1, 55);
         tc_fence_after();
-        for (int t = 0; t < nt; ++t) issue_s(t, kv);
+        if (on) issue_s(kv);
         umma_commit(&k_empty[kv % kNS5]);
-        // Event-driven issue: per tile the next action is either "PV of the next 32-key chunk of block jt" (as soon as
-        // the softmax warpgroup has stored that chunk of P: the PV MMAs of a block overlap the rest of its softmax) or
-        // "S of block jt" (right behind the last PV chunk of block jt - 1: the aliased P columns are consumed in
-        // order).  Nothing blocks: a tile that is not ready is skipped, so the two tiles never gate each other.
-        int jt[2] = {0, 0}, ch[2] = {0, 0};
-        bool s_pending[2] = {false, false};
-        int left = nt;
-        int vdone[kNS5], kdone[kNS5];
-#pragma unroll
-        for (int i = 0; i < kNS5; ++i) vdone[i] = kdone[i] = 0;
-        uint32_t spins = 0;
-        long long t_idle = 0;
-        while (left > 0) {
-          bool progress = false;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (t >= nt || jt[t] >= n_kv) continue;
-            const uint32_t cur = kv + jt[t];
-            const int st = cur % kNS5;
-            if (s_pending[t]) {
-              if (!mbar_try_wait(&k_full[st], (cur / kNS5) & 1)) continue;
-              tc_fence_after();
-              issue_s(t, cur);
-              s_pending[t] = false;
-              if (++kdone[st] == nt) {
-                umma_commit(&k_empty[st]);
-                kdone[st] = 0;
-              }
-              progress = true;
-              continue;
-            }
-            if (!mbar_try_wait(&p_full[t * 4 + ch[t]], g[t] & 1)) continue;
-            if (ch[t] == 0 && !mbar_try_wait(&v_full[st], (cur / kNS5) & 1)) continue;
-            tc_fence_after();
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t cur = kv + j;
+          const int st = cur % kNS5;
+          mbar_wait(&v_full[st], (cur / kNS5) & 1, 57);
+          if (on) {
             const uint32_t v_base = smem_u32(sV + st * kT5Bytes);
             const uint32_t lbo = ones_base - v_base;     // second N atom (columns 64..79) = the ones atom
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {             // keys 16 k .. 16 k + 15: 8 packed columns of P
-              const int k = 2 * ch[t] + kk;
-              umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
-                          make_desc_sw128(v_base + k * 2048, lbo, 1024), idesc_o, (jt[t] | k) != 0 ? 1u : 0u);
-            }
-            progress = true;
-            if (++ch[t] == 4) {
-              ch[t] = 0;
-              ++g[t];
-              if (++vdone[st] == nt) {                   // both tiles are done with V of this block
-                umma_commit(&v_empty[st]);
-                vdone[st] = 0;
-              }
-              if (jt[t] + 1 == n_kv) {
-                umma_commit(&o_full[t]);
-                ++items_t[t];
-                jt[t] = n_kv;
-                --left;
-              } else {
-                ++jt[t];
-                s_pending[t] = true;
+            for (int c = 0; c < 4; ++c) {
+              mbar_wait(&p_full[t * 4 + c], g & 1, 56);
+              tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {           // keys 16 k .. 16 k + 15: 8 packed columns of P
+                const int k = 2 * c + kk;
+                umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
+                            make_desc_sw128(v_base + k * 2048, lbo, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
               }
             }
+            ++g;
           }
-          if (progress) {
-            spins = 0;
-            t_idle = 0;
-          } else if ((++spins & 4095u) == 0u) {          // bounded: a pipeline bug ends in a trap, not a hung box
-            const long long now = clock64();
-            if (t_idle == 0) t_idle = now;
-            if (now - t_idle > VB_WAIT_TIMEOUT_CYCLES) {
-              printf("vista_b200: attn5 issuer stalled block=%d jt=(%d,%d) ch=(%d,%d)\n", blockIdx.x, jt[0], jt[1], ch[0], ch[1]);
-              __trap();
-            }
+          umma_commit(&v_empty[st]);
+          if (j + 1 == n_kv) {
+            if (on) umma_commit(&o_full[t]);
+          } else {
+            const int sn = (cur + 1) % kNS5;
+            mbar_wait(&k_full[sn], ((cur + 1) / kNS5) & 1, 58);
+            tc_fence_after();
+            if (on) issue_s(cur + 1);
+            umma_commit(&k_empty[sn]);
           }
         }
-        umma_commit(&q_empty[qb]);      // every S MMA of this item has read Q
+        umma_commit(&q_empty[qb]);      // every S MMA of this tile and item has read Q
         kv += n_kv;
       }
-      (void)items_t;
     }
   } else {
     // ------------------------------------------------------------ softmax warpgroups
@@ -291,10 +254,19 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tS = tmem_base + t * 128 + lane_off;
     const uint32_t tO = tmem_base + 256 + t * 128 + lane_off;
     uint32_t g = 0, items_done = 0;
+    if (p.pingpong && t == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");     // tile A goes first
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       int frame, head, q0;
       decode(item, frame, head, q0);
-      if (t == 1 && q0 + kT5 >= p.seq) continue;
+      if (t == 1 && q0 + kT5 >= p.seq) {          // tile B has no rows: it still passes the turn back, block by block
+        if (p.pingpong) {
+          for (int j = 0; j < n_kv; ++j) {
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            asm volatile("bar.arrive 1, 256;" ::: "memory");
+          }
+        }
+        continue;
+      }
       float m_used = -INFINITY;
       for (int j = 0; j < n_kv; ++j, ++g) {
         mbar_wait(&s_full[t], g & 1, 59);   // also implies PV_t(j-1) has completed (in-order commits)
@@ -336,6 +308,13 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
           m_used = m_new;
         }
+        // Ping-pong: the exponentials of the two tiles alternate (named barriers 1 / 2 = "A's turn" / "B's turn"), so that
+        // each warpgroup has the MUFU to itself for its 16 384 ex2 while the other one waits for its PV / S MMAs — left
+        // alone the two symmetric tiles run in phase and share the MUFU half / half during the same stretch.
+        if (p.pingpong) {
+          if (t == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
         // P = exp2(s * scale - m_used) -> packed fp16 -> columns [0, 64) of this row's own S range
 #pragma unroll
         for (int c = 0; c < 4; ++c) {      // 32 keys -> 16 packed columns
@@ -353,11 +332,26 @@ attn5_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               pw[i] = pack5_h2(p0, p1);
             }
           }
+          // the store of chunk c - 1 (and the O rescale stores above) completed while chunk c was being computed: wait for it
+          // BEFORE the next store is issued (tcgen05.wait::st covers every earlier store), then publish chunk c - 1
+          if (c > 0 && p.chunked) {
+            tmem5_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[t * 4 + c - 1]);
+          }
           tmem5_st16(tS + c * 16, pw);
-          tmem5_st_wait();                 // (also covers the O rescale stores above)
-          tc_fence_before();
-          mbar_arrive(&p_full[t * 4 + c]);
         }
+        if (p.pingpong) {                  // the other tile's turn
+          if (t == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+          else asm volatile("bar.arrive 1, 256;" ::: "memory");
+        }
+        tmem5_st_wait();
+        tc_fence_before();
+        if (!p.chunked) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) mbar_arrive(&p_full[t * 4 + c]);
+        }
+        mbar_arrive(&p_full[t * 4 + 3]);
       }
       // epilogue: O / rowsum
       mbar_wait(&o_full[t], items_done & 1, 60);
@@ -425,6 +419,12 @@ extern "C" int b200v_attention_spatial_v5(const void* q, int64_t ld_q, const voi
   p.ld_o = ld_o;
   p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  static int chunked = -1;
+  if (chunked < 0) chunked = getenv("VB_ATTN5_CHUNKED") ? atoi(getenv("VB_ATTN5_CHUNKED")) : 1;
+  p.chunked = chunked;
+  static int pingpong = -1;
+  if (pingpong < 0) pingpong = getenv("VB_ATTN5_PINGPONG") ? atoi(getenv("VB_ATTN5_PINGPONG")) : 1;
+  p.pingpong = pingpong;
   const int smem_bytes = 1024 + 1024 + (4 + 2 * kNS5 + 1) * kT5Bytes;
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Attn5Params);
   static const Kern kerns[5] = {attn5_spatial_kernel<0>, attn5_spatial_kernel<1>, attn5_spatial_kernel<2>,
@@ -445,7 +445,7 @@ extern "C" int b200v_attention_spatial_v5(const void* q, int64_t ld_q, const voi
   }
   int grid = device_sm_count();
   if (items < grid) grid = (int)items;
-  kerns[mode]<<<grid, 320, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  kerns[mode]<<<grid, 352, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

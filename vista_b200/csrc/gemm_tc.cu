@@ -44,6 +44,11 @@ struct TGParams {
   int ld_res2_b;
   float s_res2;
   float s_acc;
+  // GroupNorm statistics of the OUTPUT, fused (STATS variants): per (128-token tile, TMEM lane quadrant) column sums
+  // and sums of squares of the stored values, fp32, at stats[((tile * 4 + quad) * stats_ld + stats_col0 + n) * 2 + {0,1}];
+  // the host guarantees that a tile is 128 consecutive tokens (b200v_gemm checks the box)
+  float* stats;
+  int stats_ld, stats_col0;
 };
 
 __device__ __forceinline__ float2 unpack2(uint32_t w, int bf16) {
@@ -89,7 +94,7 @@ __device__ __forceinline__ int epi_group(int G, int wg, int k) {
 
 // NQ = 2: 10 warps are allocated as 12 (granularity 4): 65536 / 384 -> at most 168 registers per thread.
 // NQ = 4: 18 warps are allocated as 20: the bound is declared as 640 threads so that the compiler stays <= 96.
-template <int ACT_, bool RV_, int NRES_, bool GEN, bool PAIR, int NQ>
+template <int ACT_, bool RV_, int NRES_, bool GEN, bool PAIR, int NQ, bool STATS = false>
 __global__ void __launch_bounds__(NQ == 2 ? 320 : 640, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TGParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -397,6 +402,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const char* r2base = r2p + (long long)n * 2;
           const char* rvbase = reinterpret_cast<const char*>(p.rowvec) + (long long)n * 4;
           const uint2(&u1)[NI] = rpre[k & 1];
+          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};   // STATS: column sums over this lane's rows
 #pragma unroll
           for (int hb = 0; hb < NI / 4; ++hb) {
             float4 v[4], rv[4];
@@ -435,6 +441,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   o.z = fmaf(p.s_res2, b.x, o.z); o.w = fmaf(p.s_res2, b.y, o.w);
                 }
               }
+              if (STATS && ok) {
+                cs[0] += o.x; cs[1] += o.y; cs[2] += o.z; cs[3] += o.w;
+                cq[0] = fmaf(o.x, o.x, cq[0]); cq[1] = fmaf(o.y, o.y, cq[1]);
+                cq[2] = fmaf(o.z, o.z, cq[2]); cq[3] = fmaf(o.w, o.w, cq[3]);
+              }
               char* optr = obase + (long long)tok[i] * p.ldo_b;
               if (f32o) {
                 if (ok) *reinterpret_cast<float4*>(optr) = o;
@@ -442,6 +453,23 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint2 pk = make_uint2(pack2(o.x, o.y, bf16), pack2(o.z, o.w, bf16));
                 if (ok) *reinterpret_cast<uint2*>(optr) = pk;
               }
+            }
+          }
+          if (STATS) {
+            // rows of one column live in the RPI lanes ch, ch + CH, ...: fixed-order butterfly, then lane rsub == 0 holds
+            // the sums over the warp's 32 rows and writes them (one partial per tile and lane quadrant: bit-reproducible)
+#pragma unroll
+            for (int off = CH; off < 32; off <<= 1) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], off);
+                cq[c] += __shfl_xor_sync(0xffffffffu, cq[c], off);
+              }
+            }
+            if (rsub == 0 && n_ok) {
+              float* dst = p.stats + (((long long)m_blk * 4 + quad) * p.stats_ld + p.stats_col0 + n) * 2;
+              *reinterpret_cast<float4*>(dst) = make_float4(cs[0], cq[0], cs[1], cq[1]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(cs[2], cq[2], cs[3], cq[3]);
             }
           }
         }
@@ -527,7 +555,7 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   // (profiles/r01_gemm_pair_vs_single.md) the pair kernel is on par for the large-K convolutions and slower for
   // the small-K projections (the two epilogues of a pair gate each other), so it is opt-in: VB_GEMM_PAIR=1.
   static const bool pair_enabled = getenv("VB_GEMM_PAIR") && atoi(getenv("VB_GEMM_PAIR")) != 0;
-  const bool pair = pair_enabled && p.m_tiles >= 2;
+  const bool pair = pair_enabled && p.m_tiles >= 2 && !d->stats;
   const int b_rows = pair ? d->tile_n / 2 : d->tile_n;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)d->N};
@@ -565,6 +593,17 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   p.res2 = d->res2; p.ld_res2_b = (int)(d->ld_res2 * 2); p.s_res2 = d->s_res2;
   p.s_acc = d->s_acc;
   VB_REQUIRE(!(d->res2 && !d->res1), "b200v_gemm: res2 without res1");
+  p.stats = d->stats; p.stats_ld = (int)d->stats_ld; p.stats_col0 = d->stats_col0;
+  if (d->stats) {
+    VB_REQUIRE(!d->bf16 && !d->out_f32 && d->act == 0 && !d->res2 && !(d->rowvec && d->res1),
+               "b200v_gemm: fused statistics need fp16 output, act 0, <= 1 residual and no rowvec + residual");
+    VB_REQUIRE(d->stats_ld >= d->stats_col0 + d->N && d->stats_col0 % 4 == 0 && d->stats_ld % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->stats) & 15) == 0,
+               "b200v_gemm: bad stats_ld / stats_col0 / alignment");
+    VB_REQUIRE(d->a_mode == 0 || (p.BB == 1 && d->W % p.BW == 0 && d->H % p.BH == 0 && (p.BW == d->W || p.BH == 1)),
+               "b200v_gemm: fused statistics need token tiles of 128 consecutive tokens (box %d x %d x %d on %d x %d)",
+               p.BW, p.BH, p.BB, d->W, d->H);
+  }
 
   const int smem_bytes = 1024 + 1024 + p.nstages * p.stage_bytes + kStagingBytes;
   // Epilogue variant: the common fp16 feature sets are compiled in (no per-element feature tests), everything
@@ -594,9 +633,15 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   if (nq_force == 2) wide = 0;
   if (nq_force == 4) wide = 1;
   if (pair) wide = 0;
+  // fused-statistics instantiations (8 epilogue warps, single CTA): plain, one residual, row vector
+  static const Kern kStats[3] = {tapgemm_kernel<0, false, 0, false, false, 2, true>,
+                                 tapgemm_kernel<0, false, 1, false, false, 2, true>,
+                                 tapgemm_kernel<0, true, 0, false, false, 2, true>};
   static bool attr_set = false;
   static int max_clusters = 0;
   if (!attr_set) {
+    for (int i = 0; i < 3; ++i)
+      VB_CHECK_CUDA(cudaFuncSetAttribute(kStats[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     for (int q = 0; q < 2; ++q)
       for (int w = 0; w < 2; ++w)
         for (int i = 0; i < 8; ++i)
@@ -614,7 +659,12 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     }
     attr_set = true;
   }
-  if (pair) {
+  if (d->stats) {
+    const long long total = (long long)p.m_tiles * p.n_tiles;
+    int grid = device_sm_count();
+    if (total < grid) grid = (int)total;
+    kStats[d->rowvec ? 2 : (d->res1 ? 1 : 0)]<<<grid, 320, smem_bytes, stream>>>(tmA, tmB, p);
+  } else if (pair) {
     const long long total = (long long)p.m_pairs * p.n_tiles;
     int clusters = max_clusters;
     if (total < clusters) clusters = (int)total;

@@ -248,8 +248,12 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, long long tokens,
                  int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  const float* __restrict__ addvec, long long ld_addvec, int av_div, int av_mod) {
+  // Grid-stride over tokens, one warp per token, the NEXT token's row is already in flight while the current one is
+  // reduced and written (a warp that handled one token per launch left the memory system idle between its load, its two
+  // reductions and its store: 2.3 TB/s; kept busy it is an HBM stream).
   const int lane = threadIdx.x & 31;
-  const long long token = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  long long token = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (token >= tokens) return;
   const int nvec = C >> 3;
   uint4 raw[NV];
@@ -258,53 +262,68 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict
     const int vi = lane + j * 32;
     if (vi < nvec) raw[j] = __ldg(reinterpret_cast<const uint4*>(x + token * ldx + vi * 8));
   }
-  float v[NV][8];
-  const float* av = addvec ? addvec + ((token / av_div) % av_mod) * ld_addvec : nullptr;
-  float sum = 0.f;
+  while (true) {
+    const long long next = token + n_warps;
+    uint4 nxt[NV];
+    if (next < tokens) {
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int vi = lane + j * 32;
-    if (vi < nvec) {
-      h8_to_f(raw[j], v[j]);
-      if (av) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8 + 4));
-        v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
-        v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sum += v[j][i];
-    }
-  }
-  const float mean = warp_sum(sum) / (float)C;
-  float sq = 0.f;
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int vi = lane + j * 32;
-    if (vi < nvec) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = v[j][i] - mean;
-        sq += d * d;
+      for (int j = 0; j < NV; ++j) {
+        const int vi = lane + j * 32;
+        if (vi < nvec) nxt[j] = __ldg(reinterpret_cast<const uint4*>(x + next * ldx + vi * 8));
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    float v[NV][8];
+    const float* av = addvec ? addvec + ((token / av_div) % av_mod) * ld_addvec : nullptr;
+    float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int vi = lane + j * 32;
-    if (vi < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
+    for (int j = 0; j < NV; ++j) {
+      const int vi = lane + j * 32;
+      if (vi < nvec) {
+        h8_to_f(raw[j], v[j]);
+        if (av) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8 + 4));
+          v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
+          v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * gg[i] + bb[i];
-      *reinterpret_cast<uint4*>(y + token * ldy + vi * 8) = f_to_h8(o);
+        for (int i = 0; i < 8; ++i) sum += v[j][i];
+      }
     }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int vi = lane + j * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[j][i] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int vi = lane + j * 32;
+      if (vi < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * gg[i] + bb[i];
+        *reinterpret_cast<uint4*>(y + token * ldy + vi * 8) = f_to_h8(o);
+      }
+    }
+    if (next >= tokens) break;
+    token = next;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) raw[j] = nxt[j];
   }
 }
 
@@ -841,6 +860,69 @@ extern "C" int b200v_groupnorm_finalize(const double* sums, int32_t n_stat_group
   return 0;
 }
 
+// (mean, rstd) from the column partials of the producing tap-GEMM (gemm_tc.cu, STATS variants).  grid = (groups, stats);
+// thread t adds partial rows t, t + 256, ... of its group's columns in fp64, the 256 sub-sums are combined by a fixed
+// tree: bit-identical from run to run.
+namespace vb {
+__global__ void __launch_bounds__(256)
+gn_from_partials_kernel(const float* __restrict__ partials, long long ld, int rows_per_stat, int cpg, int groups, float eps,
+                        double count, float* __restrict__ mean_rstd, double* __restrict__ raw) {
+  __shared__ double red[2][256];
+  const int g = blockIdx.x, st = blockIdx.y;
+  const float* base = partials + ((long long)st * rows_per_stat * ld + (long long)g * cpg) * 2;
+  double a = 0.0, b = 0.0;
+  for (int r = threadIdx.x; r < rows_per_stat; r += 256) {
+    const float2* row = reinterpret_cast<const float2*>(base + (long long)r * ld * 2);
+    for (int c = 0; c < cpg; ++c) {
+      const float2 v = __ldg(row + c);
+      a += (double)v.x;
+      b += (double)v.y;
+    }
+  }
+  red[0][threadIdx.x] = a;
+  red[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + off];
+      red[1][threadIdx.x] += red[1][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const long long o = ((long long)st * groups + g) * 2;
+    if (raw) {
+      raw[o] = red[0][0];
+      raw[o + 1] = red[1][0];
+    } else {
+      const double mean = red[0][0] / count;
+      double var = red[1][0] / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mean_rstd[o] = (float)mean;
+      mean_rstd[o + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+}
+}  // namespace vb
+
+extern "C" int b200v_groupnorm_from_partials(const float* partials, int64_t stats_ld, int32_t n_stats, int32_t frames_per_stat,
+                                             int32_t tokens_per_frame, int32_t C, int32_t groups, float eps,
+                                             float* mean_rstd, double* raw_sums, void* stream) {
+  VB_REQUIRE(partials && (mean_rstd || raw_sums), "b200v_groupnorm_from_partials: null pointer");
+  VB_REQUIRE(n_stats > 0 && frames_per_stat > 0 && groups > 0 && C % groups == 0 && stats_ld >= C,
+             "b200v_groupnorm_from_partials: bad sizes");
+  VB_REQUIRE(tokens_per_frame % 128 == 0, "b200v_groupnorm_from_partials: tokens_per_frame=%d must be a multiple of 128",
+             tokens_per_frame);
+  const int rows_per_stat = frames_per_stat * (tokens_per_frame / 128) * 4;
+  const int cpg = C / groups;
+  dim3 grid(groups, n_stats);
+  vb::gn_from_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, stats_ld, rows_per_stat, cpg, groups, eps,
+                                                                        (double)cpg * tokens_per_frame * frames_per_stat,
+                                                                        mean_rstd, raw_sums);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int b200v_groupnorm_chunk(void) { return vb::kGnMinChunk; }
 extern "C" int b200v_groupnorm_chunk_for(int32_t frames, int32_t tokens_per_frame) {
   return vb::gn_pick_chunk(frames, tokens_per_frame);
@@ -882,17 +964,26 @@ extern "C" int b200v_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy,
   VB_REQUIRE(C % 8 == 0 && C <= 2560 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm: C=%d unsupported", C);
   VB_REQUIRE(!addvec || (av_div > 0 && av_mod > 0 && ld_addvec % 4 == 0), "layernorm: bad addvec args");
   const int wpb = 8;
-  const unsigned grid = (unsigned)((tokens + wpb - 1) / wpb);
+  const long long blocks_needed = (tokens + wpb - 1) / wpb;
   const int nv = (C / 8 + 31) / 32;
   const int ad = av_div > 0 ? av_div : 1, am = av_mod > 0 ? av_mod : 1;
+  // one resident wave of blocks (occupancy by register count), the warps stride over the tokens
 #define VB_LN_LAUNCH(NV)                                                                                             \
-  layernorm_kernel<NV><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, tokens, C, \
-                                                                     gamma, beta, eps, addvec, ld_addvec, ad, am)
-  if (nv <= 1) VB_LN_LAUNCH(1);
-  else if (nv <= 2) VB_LN_LAUNCH(2);
-  else if (nv <= 3) VB_LN_LAUNCH(3);
-  else if (nv <= 5) VB_LN_LAUNCH(5);
-  else VB_LN_LAUNCH(10);
+  {                                                                                                                  \
+    static int per_sm = 0;                                                                                           \
+    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_kernel<NV>, wpb * 32, 0) != \
+                            cudaSuccess || per_sm <= 0))                                                            \
+      per_sm = 2;                                                                                                    \
+    long long blocks = (long long)vb::device_sm_count() * per_sm;                                                    \
+    if (blocks > blocks_needed) blocks = blocks_needed;                                                              \
+    layernorm_kernel<NV><<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(                                   \
+        (const __half*)x, ldx, (__half*)y, ldy, tokens, C, gamma, beta, eps, addvec, ld_addvec, ad, am);             \
+  }
+  if (nv <= 1) VB_LN_LAUNCH(1)
+  else if (nv <= 2) VB_LN_LAUNCH(2)
+  else if (nv <= 3) VB_LN_LAUNCH(3)
+  else if (nv <= 5) VB_LN_LAUNCH(5)
+  else VB_LN_LAUNCH(10)
 #undef VB_LN_LAUNCH
   VB_CHECK_CUDA(cudaGetLastError());
   return 0;

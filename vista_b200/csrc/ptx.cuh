@@ -39,6 +39,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (mbarrier.test_wait returns at once; try_wait may suspend the thread for a system-dependent time,
+// which is wrong for a thread that polls SEVERAL barriers in turn).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must end in a trap (test failure), never in a hung GPU box.  The clock is
 // consulted only every 4096 failed probes.
 #ifndef VB_WAIT_TIMEOUT_CYCLES
@@ -271,7 +284,14 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int bf
 }
 
 // ------------------------------------------------------------------ misc math
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with two MUFU operations (ex2, rcp) and no IEEE division sequence; relative error ~2^-22, far below
+// the fp16 rounding of every tensor this is stored to
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // erf-GELU via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7; measured |gelu error| <= 4.3e-7, below the
 // fp16 rounding of the output): erfc(a) = poly(t) * exp(-a^2), t = 1/(1 + p a), a = |x|/sqrt(2).

@@ -103,11 +103,23 @@ class DiffusionEngine(nn.Module):
         dec = self.first_stage_model.decoder
         if not isinstance(dec, VideoDecoder):
             raise NotImplementedError("decode_first_stage needs vista_b200.vae.VideoDecoder as decoder_config.target")
-        if getattr(self.model, "frame_sharded", False):     # one clip on several ranks: deal the chunks out as well
-            from .vae import decode_first_stage_parallel
+        if getattr(self.model, "frame_sharded", False):     # one clip on several ranks: spread the decode as well
+            import os
+            import torch.distributed as dist
+            from .vae import _decode_chunks, decode_first_stage_parallel
+            group = getattr(self.model, "world_group", None)
+            n_chunks = len(_decode_chunks(z.shape[0], self.en_and_decode_n_samples_a_time or z.shape[0], overlap))
+            mode = os.environ.get("VISTA_B200_SHARDED_DECODE", "auto")
+            if mode == "1" or (mode == "auto" and dist.get_world_size(group) > n_chunks):
+                # more ranks than chunks: shard the FRAMES of every chunk (sharded.ShardedDecoderRuntime)
+                from .sharded import ShardedDecoderRuntime, decode_first_stage_sharded
+                srt = getattr(dec, "_sharded_rt", None)
+                if srt is None or srt.dev != torch.device(z.device) or srt.group is not group:
+                    srt = dec._sharded_rt = ShardedDecoderRuntime(dec.b200_config, dec.state_dict(), z.device, group=group)
+                return decode_first_stage_sharded(srt, z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap)
+            # as many chunks as ranks (or fewer ranks): deal whole chunks out, bit-identical to the serial decode
             return decode_first_stage_parallel(dec.runtime(z.device), z, self.scale_factor,
-                                               self.en_and_decode_n_samples_a_time, overlap,
-                                               group=getattr(self.model, "world_group", None))
+                                               self.en_and_decode_n_samples_a_time, overlap, group=group)
         return _decode_first_stage(dec.runtime(z.device), z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap)
 
     @torch.no_grad()

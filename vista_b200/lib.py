@@ -83,6 +83,7 @@ class GemmDesc(C.Structure):
         ("res1", C.c_void_p), ("ld_res1", C.c_int64), ("s_res1", C.c_float),
         ("res2", C.c_void_p), ("ld_res2", C.c_int64), ("s_res2", C.c_float),
         ("s_acc", C.c_float),
+        ("stats", C.c_void_p), ("stats_ld", C.c_int64), ("stats_col0", C.c_int32),
     ]
 
 
@@ -99,6 +100,7 @@ SIGNATURES = {
     "b200v_attention_spatial_v4": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v5": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
+    "b200v_groupnorm_from_partials": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P],
     "b200v_groupnorm_chunk": [],
     "b200v_groupnorm_chunk_for": [C.c_int32, C.c_int32],
     "b200v_groupnorm_sums": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P],

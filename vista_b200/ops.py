@@ -104,6 +104,17 @@ def pick_box(W: int, H: int, NB: int) -> Tuple[int, int, int]:
     return best
 
 
+def stats_box(W: int, H: int, NB: int) -> Optional[Tuple[int, int, int]]:
+    """Token tile of 128 CONSECUTIVE tokens (whole image rows, or a segment of one row) — what the fused GroupNorm
+    statistics need so that tile i covers tokens [128 i, 128 i + 128) in every producer of a tensor; None if the geometry
+    has no such tiling (then the statistics take their own pass)."""
+    if W >= 128:
+        return (128, 1, 1) if W % 128 == 0 else None
+    if 128 % W == 0 and H % (128 // W) == 0:
+        return (W, 128 // W, 1)
+    return None
+
+
 def pick_tile_n(N: int, geglu: bool = False) -> int:
     """tile_n <= 256 (multiple of 32, of 64 for GEGLU) minimising the MMA time of one row of n-tiles under the
     measured cost of a 128 x tile_n x 16 tcgen05.mma, t(n) = 61 + 0.22 * max(n, 128) ns
@@ -127,9 +138,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
          rowvec: Optional[torch.Tensor] = None, rv_div: int = 1, rv_mod: int = 1,
          res1: Optional[torch.Tensor] = None, s_res1: float = 1.0,
          res2: Optional[torch.Tensor] = None, s_res2: float = 1.0,
-         s_acc: float = 1.0, act: int = 0, tile_n: Optional[int] = None, cin: Optional[int] = None) -> torch.Tensor:
+         s_acc: float = 1.0, act: int = 0, tile_n: Optional[int] = None, cin: Optional[int] = None,
+         stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(tap-GEMM(a, w)).  ``a``: [tokens, >=cin] fp16 view; ``w``: [N, ntaps*cin] fp16;
-    ``geom`` = (W, H, NB) turns on image taps (zero padded); act 2 = GEGLU (out has N/2 columns)."""
+    ``geom`` = (W, H, NB) turns on image taps (zero padded); act 2 = GEGLU (out has N/2 columns).
+    ``stats`` = partials [tokens/128*4, N, 2] fp32 (may be a column slice of a wider matrix): the epilogue also writes the
+    column sums / sums of squares of the output (GroupNorm statistics of the consumer without a pass over the tensor);
+    the token tiles are then the 128-consecutive-token ones of stats_box()."""
     tokens, lda = _rows(a)
     N, K = w.shape
     ntaps = len(taps)
@@ -144,7 +159,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
         d.a_mode = 1
         d.W, d.H, d.NB = geom
         assert geom[0] * geom[1] * geom[2] == tokens
-        d.box_w, d.box_h, d.box_b = pick_box(*geom)
+        d.box_w, d.box_h, d.box_b = pick_box(*geom) if stats is None else stats_box(*geom)
     d.cin, d.ntaps = cin, ntaps
     for i, (dh, dw) in enumerate(taps):
         d.dh[i], d.dw[i] = dh, dw
@@ -161,6 +176,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
     if res2 is not None:
         d.res2, d.ld_res2, d.s_res2 = res2.data_ptr(), res2.stride(0), s_res2
     d.s_acc = s_acc
+    if stats is not None:      # [tokens/128*4, >= N, 2] fp32 view (possibly a column slice of a wider partial matrix)
+        assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[2] == 2 and stats.stride(2) == 1 \
+            and stats.stride(1) == 2 and stats.stride(0) % 2 == 0 and stats.shape[1] >= (N // 2 if act == 2 else N)
+        assert stats.shape[0] >= -(-tokens // 128) * 4
+        d.stats, d.stats_ld, d.stats_col0 = stats.data_ptr(), stats.stride(0) // 2, 0
     _count()
     n_out = N // 2 if act == 2 else N
     _prof_begin("gemm", f"M={tokens} N={N} K={K} taps={ntaps} act={act}", 2.0 * tokens * N * K,
@@ -172,13 +192,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
     return out
 
 
-ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "3"))   # 3: two CTAs/SM, two threads per row (default); 2: ping-pong tiles; 1: first generation
+# Spatial-attention kernel generation.  0 (default): by shape — v5 (persistent, two query tiles per CTA in ping-pong, P in
+# tensor memory) for long sequences, v3 (one tile per CTA, two CTAs per SM) for the short ones of the inner levels;
+# 1 / 2 / 3 / 4 / 5 force one generation.
+ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "0"))
 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
     l = _lib.load()
     fn = {1: l.b200v_attention_spatial, 2: l.b200v_attention_spatial_v2, 3: l.b200v_attention_spatial_v3,
-          4: l.b200v_attention_spatial_v4, 5: l.b200v_attention_spatial_v5}[impl or ATTN_IMPL]
+          4: l.b200v_attention_spatial_v4, 5: l.b200v_attention_spatial_v5}[impl or ATTN_IMPL or (5 if seq >= 2048 else 3)]
     _count(1)
     _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
                 2.0 * 4 * frames * seq * heads * 64)
@@ -249,6 +272,37 @@ def groupnorm(x, y, frames: int, tokens_per_frame: int, gamma, beta, eps: float,
                "b200v_groupnorm_apply")
     _prof_end()
     _trace(f"groupnorm fps={frames_per_stat}", y)
+    return y
+
+
+def groupnorm_from_partials(partials, frames: int, tokens_per_frame: int, Cc: int, eps: float, stats: Optional[torch.Tensor],
+                            frames_per_stat: int = 1, groups: int = 32, raw_sums: Optional[torch.Tensor] = None):
+    """(mean, rstd) [frames/frames_per_stat, groups, 2] from the column partials the producing GEMM(s) wrote; raw_sums
+    (fp64) instead for the frame-sharded GroupNorm."""
+    _count(1)
+    _prof_begin("groupnorm", f"from_partials tokens={frames * tokens_per_frame} C={Cc} fps={frames_per_stat}", 0.0,
+                4.0 * 2 * (frames * tokens_per_frame // 32) * Cc)
+    assert partials.stride(1) == 2 and partials.stride(2) == 1 and partials.shape[1] == Cc
+    _lib.check(_lib.load().b200v_groupnorm_from_partials(partials.data_ptr(), partials.stride(0) // 2, frames // frames_per_stat,
+                                                         frames_per_stat, tokens_per_frame, Cc, groups, eps, _ptr(stats),
+                                                         _ptr(raw_sums), _stream()), "b200v_groupnorm_from_partials")
+    _prof_end()
+    return stats
+
+
+def groupnorm_apply(x, y, frames: int, tokens_per_frame: int, gamma, beta, silu: bool, stats: torch.Tensor,
+                    frames_per_stat: int = 1, groups: int = 32):
+    """The apply half of GroupNorm alone (statistics already in ``stats``)."""
+    Cc = gamma.numel()
+    _count(1)
+    _prof_begin("groupnorm", f"apply tokens={frames * tokens_per_frame} C={Cc} fps={frames_per_stat}", 0.0,
+                2.0 * 2 * frames * tokens_per_frame * Cc)
+    _lib.check(_lib.load().b200v_groupnorm_apply(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), frames,
+                                                 tokens_per_frame, Cc, groups, frames_per_stat, stats.data_ptr(),
+                                                 gamma.data_ptr(), beta.data_ptr(), int(silu), _stream()),
+               "b200v_groupnorm_apply")
+    _prof_end()
+    _trace(f"groupnorm(apply) fps={frames_per_stat}", y)
     return y
 
 

@@ -111,7 +111,12 @@ class ShardedUNetRuntime(UNetRuntime):
             cond["pos"][t.prefix] = full[self.t0:self.t1]          # rows of the local frames, contiguous view
 
     # ------------------------------------------------------------------ temporal GroupNorm
-    def _gn_temporal(self, x, y, B, hw, norm, eps, silu, idx, fps):
+    def _fuse_stats(self, B, h, w) -> bool:
+        # the (3,1,1) convolutions get their halo corrections AFTER the main launch: statistics taken in its epilogue would
+        # miss them.  Frame-sharded steps keep the separate statistics pass.
+        return False
+
+    def _gn_temporal(self, x, y, B, hw, norm, eps, silu, idx, fps, part=None):
         nb = B // fps
         Cc = norm[0].numel()
         sums = self.buf(f"gn.sums{nb}", nb * self.cfg.num_groups, 2, torch.float64)
@@ -235,9 +240,12 @@ class ShardedDecoderRuntime(DecoderRuntime):
         self.next = self._to_global(self.rank + 1) if self.active and self.rank < last else None
 
     # temporal GroupNorm: one statistic over ALL frames of the chunk
-    def _gn(self, x, y, T, hw, norm, eps, idx, fps=1):
+    def _fuse_stats(self, T, h, w) -> bool:
+        return False        # halo corrections land after the main (3,1,1) launch: keep the separate statistics pass
+
+    def _gn(self, x, y, T, hw, norm, eps, idx, fps=1, part=None, silu=True):
         if fps == 1:
-            return super()._gn(x, y, T, hw, norm, eps, idx, fps)
+            return super()._gn(x, y, T, hw, norm, eps, idx, fps, silu=silu)
         Cc, G = norm[0].numel(), self.cfg.num_groups
         sums = self.buf("gn.sums", G, 2, torch.float64)
         ops.groupnorm_sums(x, T, hw, Cc, sums, T, groups=G, ws=self.gn_ws)
@@ -303,7 +311,7 @@ class ShardedDecoderRuntime(DecoderRuntime):
         x = ops.conv3x3_small_cin(z_tokens, cfg.z_channels, self.conv_in_w, self.conv_in_b,
                                   self.buf("d.in", T * h * w, self.plan.block_in), T, h, w)
         x = self._resblock(self.res[self.plan.mid[0].prefix], x, T, h, w, "d.r0")
-        x = self._attn(x, T, h, w)
+        x, _ = self._attn(x, T, h, w)
         x = self._resblock(self.res[self.plan.mid[1].prefix], x, T, h, w, "d.r1")
         for blocks, up, ch in self.plan.levels:
             for bi, rb in enumerate(blocks):

@@ -19,6 +19,7 @@ hand-written kernels.  Design points (DESIGN.md has the full list):
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -36,6 +37,8 @@ class Lin:
     tile_n: int
     geglu: bool = False
 
+
+FUSE_GN_STATS = os.environ.get("VISTA_B200_FUSE_GN", "1") != "0"   # GroupNorm statistics from the producer's epilogue
 
 IN_PAD = 64   # token rows of the network input: 8 channels used, zero padded to one 64-channel K chunk
 
@@ -169,16 +172,34 @@ class UNetRuntime:
     def gemm(self, a, lin: Lin, out, **kw):
         return ops.gemm(a, lin.w, out, bias=lin.b, tile_n=lin.tile_n, act=2 if lin.geglu else kw.pop("act", 0), **kw)
 
-    def _gn(self, x, y, B, hw, norm, eps, silu, idx, fps=1):
+    def _gn(self, x, y, B, hw, norm, eps, silu, idx, fps=1, part=None):
+        """GroupNorm32 (+ SiLU).  ``part``: column partials of x written by its producing GEMM(s) — the statistics then
+        cost one small reduction instead of a pass over x (util.py:214-216 reads x three times in the reference)."""
         if fps != 1:
-            return self._gn_temporal(x, y, B, hw, norm, eps, silu, idx, fps)
-        return ops.groupnorm(x, y, B, hw, norm[0], norm[1], eps, silu, self.gn_stats[idx, : B // fps],
-                             frames_per_stat=fps, groups=self.cfg.num_groups, ws=self.gn_ws)
+            return self._gn_temporal(x, y, B, hw, norm, eps, silu, idx, fps, part)
+        stats = self.gn_stats[idx, : B // fps]
+        if part is None:
+            return ops.groupnorm(x, y, B, hw, norm[0], norm[1], eps, silu, stats, frames_per_stat=fps,
+                                 groups=self.cfg.num_groups, ws=self.gn_ws)
+        ops.groupnorm_from_partials(part, B, hw, norm[0].numel(), eps, stats, fps, self.cfg.num_groups)
+        return ops.groupnorm_apply(x, y, B, hw, norm[0], norm[1], silu, stats, fps, self.cfg.num_groups)
 
-    def _gn_temporal(self, x, y, B, hw, norm, eps, silu, idx, fps):
+    def _gn_temporal(self, x, y, B, hw, norm, eps, silu, idx, fps, part=None):
         """GroupNorm whose statistic spans the frames of a clip (video_model.py:67-72)."""
-        return ops.groupnorm(x, y, B, hw, norm[0], norm[1], eps, silu, self.gn_stats[idx, : B // fps],
-                             frames_per_stat=fps, groups=self.cfg.num_groups, ws=self.gn_ws)
+        stats = self.gn_stats[idx, : B // fps]
+        if part is None:
+            return ops.groupnorm(x, y, B, hw, norm[0], norm[1], eps, silu, stats, frames_per_stat=fps,
+                                 groups=self.cfg.num_groups, ws=self.gn_ws)
+        ops.groupnorm_from_partials(part, B, hw, norm[0].numel(), eps, stats, fps, self.cfg.num_groups)
+        return ops.groupnorm_apply(x, y, B, hw, norm[0], norm[1], silu, stats, fps, self.cfg.num_groups)
+
+    def part(self, name: str, tokens: int, cols: int) -> torch.Tensor:
+        """Persistent [tokens/128*4, cols, 2] fp32 matrix of GroupNorm column partials (ops.gemm(stats=...))."""
+        key = ("part." + name, tokens, cols)
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = torch.zeros(-(-tokens // 128) * 4, cols, 2, dtype=torch.float32, device=self.dev)
+        return t
 
     def _ln(self, x, y, norm, **kw):
         return ops.layernorm(x, y, norm[0], norm[1], 1e-5, **kw)
@@ -228,23 +249,33 @@ class UNetRuntime:
         self.cond = cond
 
     # ------------------------------------------------------------------ layers
-    def _resblock(self, L, x, dst, B, h, w):
+    def _fuse_stats(self, B, h, w) -> bool:
+        """GroupNorm statistics come out of the producing GEMM's epilogue where the token tiles are runs of 128 consecutive
+        tokens (ops.stats_box): 72 x 128 and 36 x 64 of the BASELINE shape, every level of the decoder."""
+        return FUSE_GN_STATS and ops.stats_box(w, h, B) is not None
+
+    def _resblock(self, L, x, dst, B, h, w, xp=None, dp=None):
+        """xp: column partials of x (None: the statistics of x take their own pass); dp: where to put those of dst."""
         rb: ResBlockSpec = L["spec"]
         T, hw, M, nb = self.T, h * w, B * h * w, B // self.T
         gi = L["gn_idx"]
-        a1 = self._gn(x, self.buf("rb.a1", M, rb.cin), B, hw, L["gn1"], 1e-5, True, gi)
+        fuse = self._fuse_stats(B, h, w)
+        p1 = self.part("rb.h1", M, rb.cout) if fuse else None
+        p2 = self.part("rb.xsp", M, rb.cout) if fuse else None
+        a1 = self._gn(x, self.buf("rb.a1", M, rb.cin), B, hw, L["gn1"], 1e-5, True, gi, part=xp)
         h1 = self.gemm(a1, L["conv1"], self.buf("rb.h1", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, B),
-                       rowvec=self.emb_out[:, L["emb_off"]:L["emb_off"] + rb.cout], rv_div=hw, rv_mod=B)
-        a2 = self._gn(h1, self.buf("rb.a2", M, rb.cout), B, hw, L["gn2"], 1e-5, True, gi + 1)
+                       rowvec=self.emb_out[:, L["emb_off"]:L["emb_off"] + rb.cout], rv_div=hw, rv_mod=B, stats=p1)
+        a2 = self._gn(h1, self.buf("rb.a2", M, rb.cout), B, hw, L["gn2"], 1e-5, True, gi + 1, part=p1)
         xs = x if L["skip"] is None else self.gemm(x, L["skip"], self.buf("rb.xs", M, rb.cout))
-        xsp = self.gemm(a2, L["conv2"], self.buf("rb.xsp", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, B), res1=xs)
+        xsp = self.gemm(a2, L["conv2"], self.buf("rb.xsp", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, B), res1=xs,
+                        stats=p2)
         # temporal ResBlock: GroupNorm over (C/32, T, H, W), (3,1,1) conv over frames, AlphaBlender
-        a3 = self._gn(xsp, self.buf("rb.a1", M, rb.cout), B, hw, L["tgn1"], 1e-5, True, gi + 2, fps=T)
+        a3 = self._gn(xsp, self.buf("rb.a1", M, rb.cout), B, hw, L["tgn1"], 1e-5, True, gi + 2, fps=T, part=p2)
         h2 = self._tconv(a3, L["tconv1"], self.buf("rb.h1", M, rb.cout), hw, nb,
-                         rowvec=self.emb_out[:, L["embt_off"]:L["embt_off"] + rb.cout], rv_div=hw, rv_mod=B)
-        a4 = self._gn(h2, self.buf("rb.a2", M, rb.cout), B, hw, L["tgn2"], 1e-5, True, gi + 3, fps=T)
+                         rowvec=self.emb_out[:, L["embt_off"]:L["embt_off"] + rb.cout], rv_div=hw, rv_mod=B, stats=p1)
+        a4 = self._gn(h2, self.buf("rb.a2", M, rb.cout), B, hw, L["tgn2"], 1e-5, True, gi + 3, fps=T, part=p1)
         # out = alpha*xsp + (1-alpha)*(xsp + conv) = xsp + (1-alpha)*(conv + bias)      (util.py:317)
-        self._tconv(a4, L["tconv2"], dst, hw, nb, s_acc=1.0 - L["alpha"], res1=xsp)
+        self._tconv(a4, L["tconv2"], dst, hw, nb, s_acc=1.0 - L["alpha"], res1=xsp, stats=dp if fuse else None)
         return dst
 
     def _tconv(self, a, lin: Lin, out, hw: int, nb: int, **epi):
@@ -254,12 +285,12 @@ class UNetRuntime:
     def _attn_temporal(self, qkv, o, nb: int, hw: int, heads: int, Cc: int):
         return ops.attention_temporal(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], o, nb, self.T, hw, heads)
 
-    def _svt(self, L, x, dst, B, h, w):
+    def _svt(self, L, x, dst, B, h, w, xp=None, dp=None):
         t: SVTSpec = L["spec"]
         T, hw, M, nb, Cc = self.T, h * w, B * h * w, B // self.T, t.ch
         p = t.prefix
         al = L["alpha"]
-        xn = self._gn(x, self.buf("tr.n", M, Cc), B, hw, L["norm"], 1e-6, False, L["gn_idx"])
+        xn = self._gn(x, self.buf("tr.n", M, Cc), B, hw, L["norm"], 1e-6, False, L["gn_idx"], part=xp)
         t0 = self.gemm(xn, L["proj_in"], self.buf("tr.t0", M, Cc))
         # spatial block: self-attn, (constant) cross-attn, GEGLU FF           (attention.py:514-524)
         n = self._ln(t0, self.buf("tr.n", M, Cc), L["ln1"])
@@ -283,22 +314,23 @@ class UNetRuntime:
         g = self.gemm(n, L["tff1"], self.buf("tr.g", M, 4 * Cc))
         # x = alpha*t2 + (1-alpha)*(ff(...) + u2)                               (util.py:317)
         x3 = self.gemm(g, L["tff2"], self.buf("tr.u1", M, Cc), s_acc=1.0 - al, res1=u2, s_res1=1.0 - al, res2=t2, s_res2=al)
-        self.gemm(x3, L["proj_out"], dst, res1=x)
+        self.gemm(x3, L["proj_out"], dst, res1=x, stats=dp if self._fuse_stats(B, h, w) else None)
         return dst
 
-    def _down(self, L, x, dst, B, h, w):
+    def _down(self, L, x, dst, B, h, w, dp=None):
         c: ConvSpec = L["spec"]
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         col = self.buf("down.col", B * ho * wo, 9 * c.cin)
         ops.im2col_s2(x, col, B, h, w, c.cin)
-        self.gemm(col, L["conv"], dst)
+        self.gemm(col, L["conv"], dst, stats=dp if self._fuse_stats(B, ho, wo) else None)
         return dst
 
-    def _up(self, L, x, dst, B, h, w):
+    def _up(self, L, x, dst, B, h, w, dp=None):
         c: ConvSpec = L["spec"]
         up = self.buf("up.x", B * 4 * h * w, c.cin)
         ops.upsample2x(x, up, B, h, w, c.cin)
-        self.gemm(up, L["conv"], dst, taps=ops.TAPS_3X3, geom=(2 * w, 2 * h, B))
+        self.gemm(up, L["conv"], dst, taps=ops.TAPS_3X3, geom=(2 * w, 2 * h, B),
+                  stats=dp if self._fuse_stats(B, 2 * h, 2 * w) else None)
         return dst
 
     # ------------------------------------------------------------------ forward
@@ -354,49 +386,76 @@ class UNetRuntime:
             cat_bufs.append(self.buf(f"cat{j}", B * sh * sw, ch_in_h[j] + cskip))
             sizes.append((sh, sw))
 
-        def run_block(blk, x, dst, bh, bw):
+        def run_block(blk, x, dst, bh, bw, xp=None, dp=None):
+            """xp: GroupNorm column partials of x (or None); dp: partial view to fill for dst (or None).  Returns
+            (dst tensor, True if dp was filled)."""
             n_layers = len(blk.layers)
+            filled = False
             for li, layer in enumerate(blk.layers):
                 last = li == n_layers - 1
                 L = self.layers[layer.prefix]
-                if isinstance(layer, ResBlockSpec):
-                    d = dst if last else self.buf("blk.tmp%d" % li, B * bh * bw, layer.cout)
-                    x = self._resblock(L, x, d, B, bh, bw)
-                elif isinstance(layer, SVTSpec):
-                    d = dst if last else self.buf("blk.tmp%d" % li, B * bh * bw, layer.ch)
-                    x = self._svt(L, x, d, B, bh, bw)
+                if isinstance(layer, ResBlockSpec) or isinstance(layer, SVTSpec):
+                    cch = layer.cout if isinstance(layer, ResBlockSpec) else layer.ch
+                    fuse = self._fuse_stats(B, bh, bw)
+                    d = dst if last else self.buf("blk.tmp%d" % li, B * bh * bw, cch)
+                    p_out = (dp if last else self.part("blk.tmp%d" % li, B * bh * bw, cch)) if fuse else None
+                    fn = self._resblock if isinstance(layer, ResBlockSpec) else self._svt
+                    x = fn(L, x, d, B, bh, bw, xp=xp, dp=p_out)
+                    xp = p_out
+                    filled = p_out is not None
                 elif layer.kind == "down":
-                    x = self._down(L, x, dst, B, bh, bw)
+                    ho, wo = (bh - 1) // 2 + 1, (bw - 1) // 2 + 1
+                    x = self._down(L, x, dst, B, bh, bw, dp=dp)
+                    filled = dp is not None and self._fuse_stats(B, ho, wo)
                 elif layer.kind == "up":
-                    x = self._up(L, x, dst, B, bh, bw)
+                    x = self._up(L, x, dst, B, bh, bw, dp=dp)
+                    filled = dp is not None and self._fuse_stats(B, 2 * bh, 2 * bw)
                 elif layer.kind == "conv_in":
                     if x.stride(0) == IN_PAD:      # zero-padded rows: the input conv runs on the tensor cores
                         a = x.as_strided((x.shape[0], IN_PAD), (IN_PAD, 1))
-                        x = self.gemm(a, L["conv"], dst, taps=ops.TAPS_3X3, geom=(bw, bh, B))
+                        fuse = dp is not None and self._fuse_stats(B, bh, bw)
+                        x = self.gemm(a, L["conv"], dst, taps=ops.TAPS_3X3, geom=(bw, bh, B), stats=dp if fuse else None)
+                        filled = fuse
                     else:
                         x = ops.conv3x3_small_cin(x, layer.cin, L["w"], L["b"], dst, B, bh, bw)
-            return x
+            return x, filled
 
+        # GroupNorm column partials of the skip-concat buffers: two producers (h half, skip half) fill one matrix
+        cat_parts = [self.part(f"cat{j}", cat_bufs[j].shape[0], cat_bufs[j].shape[1]) if self._fuse_stats(B, *sizes[j]) else None
+                     for j in range(n_out)]
+        cat_ok = [[False, False] for _ in range(n_out)]
         # --- input blocks: block i writes into the skip slice of output block (n-1-i)
-        cur = x_tokens
+        cur, cur_p = x_tokens, None
         hh, ww = h, w                      # size of the tensor entering the block
         for i, blk in enumerate(plan.input_blocks):
             j = n_out - 1 - i
-            cur = run_block(blk, cur, cat_bufs[j][:, ch_in_h[j]:], hh, ww)
+            dp = cat_parts[j][:, ch_in_h[j]:] if cat_parts[j] is not None else None
+            cur, cat_ok[j][1] = run_block(blk, cur, cat_bufs[j][:, ch_in_h[j]:], hh, ww, xp=cur_p, dp=dp)
+            cur_p = dp if cat_ok[j][1] else None
             hh, ww = in_sizes[i]
         # --- middle block -> h slice of output block 0
-        cur = run_block(plan.middle_block, cur, cat_bufs[0][:, :ch_in_h[0]], hh, ww)
+        dp = cat_parts[0][:, :ch_in_h[0]] if cat_parts[0] is not None else None
+        cur, cat_ok[0][0] = run_block(plan.middle_block, cur, cat_bufs[0][:, :ch_in_h[0]], hh, ww, xp=cur_p, dp=dp)
         # --- output blocks
+        last_p = None
         for j, blk in enumerate(plan.output_blocks):
             bh, bw = sizes[j]
             if j + 1 < n_out:
                 dst = cat_bufs[j + 1][:, :ch_in_h[j + 1]]
+                dp = cat_parts[j + 1][:, :ch_in_h[j + 1]] if cat_parts[j + 1] is not None else None
             else:
-                dst = self.buf("unet.last", B * bh * bw, blk.layers[-1].cout if not isinstance(blk.layers[-1], SVTSpec) else blk.layers[-1].ch)
-            cur = run_block(blk, cat_bufs[j], dst, bh, bw)
+                cl = blk.layers[-1].cout if not isinstance(blk.layers[-1], SVTSpec) else blk.layers[-1].ch
+                dst = self.buf("unet.last", B * bh * bw, cl)
+                dp = self.part("unet.last", B * bh * bw, cl) if self._fuse_stats(B, bh, bw) else None
+            xp = cat_parts[j] if (cat_parts[j] is not None and all(cat_ok[j])) else None
+            cur, ok = run_block(blk, cat_bufs[j], dst, bh, bw, xp=xp, dp=dp)
+            if j + 1 < n_out:
+                cat_ok[j + 1][0] = ok
+            else:
+                last_p = dp if ok else None
         # --- out: GroupNorm32 -> SiLU -> conv3x3(320 -> 4)                      (video_model.py:434-440,502-503)
         M = B * h * w
-        a = self._gn(cur, self.buf("out.a", M, mc), B, h * w, self.out_norm, 1e-5, True, self.out_gn_idx)
+        a = self._gn(cur, self.buf("out.a", M, mc), B, h * w, self.out_norm, 1e-5, True, self.out_gn_idx, part=last_p)
         if net_out is None:
             net_out = self.buf("unet.out", M, 8, torch.float32)
         self.gemm(a, self.out_conv, net_out, taps=ops.TAPS_3X3, geom=(w, h, B))

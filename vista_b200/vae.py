@@ -100,34 +100,57 @@ class DecoderRuntime:
     def gemm(self, a, lin: Lin, out, **kw):
         return ops.gemm(a, lin.w, out, bias=lin.b, tile_n=lin.tile_n, **kw)
 
-    def _gn(self, x, y, T, hw, norm, eps, idx, fps=1):
-        return ops.groupnorm(x, y, T, hw, norm[0], norm[1], eps, True, self.gn_stats[idx, : T // fps],
-                             frames_per_stat=fps, groups=self.cfg.num_groups, ws=self.gn_ws)
+    def _gn(self, x, y, T, hw, norm, eps, idx, fps=1, part=None, silu=True):
+        """GroupNorm (+ swish).  part: column partials of x from its producing GEMM (ops.gemm(stats=...)): the statistics
+        are then one small reduction instead of a pass over x."""
+        stats = self.gn_stats[idx, : T // fps]
+        if part is None:
+            return ops.groupnorm(x, y, T, hw, norm[0], norm[1], eps, silu, stats, frames_per_stat=fps,
+                                 groups=self.cfg.num_groups, ws=self.gn_ws)
+        ops.groupnorm_from_partials(part, T, hw, norm[0].numel(), eps, stats, fps, self.cfg.num_groups)
+        return ops.groupnorm_apply(x, y, T, hw, norm[0], norm[1], silu, stats, fps, self.cfg.num_groups)
 
-    def _resblock(self, L, x, T, h, w, name):
+    def part(self, name: str, tokens: int, cols: int) -> torch.Tensor:
+        key = ("part." + name, tokens, cols)
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = torch.zeros(-(-tokens // 128) * 4, cols, 2, dtype=torch.float32, device=self.dev)
+        return t
+
+    def _fuse_stats(self, T, h, w) -> bool:
+        from .unet import FUSE_GN_STATS
+        return FUSE_GN_STATS and ops.stats_box(w, h, T) is not None
+
+    def _resblock(self, L, x, T, h, w, name, xp=None):
+        """Returns (output, its GroupNorm column partials or None); xp: those of x."""
         rb: DecResBlockSpec = L["spec"]
         hw, M, gi = h * w, T * h * w, L["gn_idx"]
-        a1 = self._gn(x, self.buf("d.a1", M, rb.cin), T, hw, L["gn1"], 1e-6, gi)
-        h1 = self.gemm(a1, L["conv1"], self.buf("d.h1", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, T))
-        a2 = self._gn(h1, self.buf("d.a2", M, rb.cout), T, hw, L["gn2"], 1e-6, gi + 1)
+        fuse = self._fuse_stats(T, h, w)
+        p1 = self.part("d.h1", M, rb.cout) if fuse else None
+        p2 = self.part("d.xsp", M, rb.cout) if fuse else None
+        pd = self.part(name, M, rb.cout) if fuse else None
+        a1 = self._gn(x, self.buf("d.a1", M, rb.cin), T, hw, L["gn1"], 1e-6, gi, part=xp)
+        h1 = self.gemm(a1, L["conv1"], self.buf("d.h1", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, T), stats=p1)
+        a2 = self._gn(h1, self.buf("d.a2", M, rb.cout), T, hw, L["gn2"], 1e-6, gi + 1, part=p1)
         xs = x if L["skip"] is None else self.gemm(x, L["skip"], self.buf("d.xs", M, rb.cout))
-        xsp = self.gemm(a2, L["conv2"], self.buf("d.xsp", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, T), res1=xs)
-        a3 = self._gn(xsp, self.buf("d.a1", M, rb.cout), T, hw, L["tgn1"], 1e-5, gi + 2, fps=T)
-        h2 = self.gemm(a3, L["tconv1"], self.buf("d.h1", M, rb.cout), taps=ops.TAPS_T3, geom=(hw, T, 1))
-        a4 = self._gn(h2, self.buf("d.a2", M, rb.cout), T, hw, L["tgn2"], 1e-5, gi + 3, fps=T)
+        xsp = self.gemm(a2, L["conv2"], self.buf("d.xsp", M, rb.cout), taps=ops.TAPS_3X3, geom=(w, h, T), res1=xs, stats=p2)
+        a3 = self._gn(xsp, self.buf("d.a1", M, rb.cout), T, hw, L["tgn1"], 1e-5, gi + 2, fps=T, part=p2)
+        h2 = self.gemm(a3, L["tconv1"], self.buf("d.h1", M, rb.cout), taps=ops.TAPS_T3, geom=(hw, T, 1), stats=p1)
+        a4 = self._gn(h2, self.buf("d.a2", M, rb.cout), T, hw, L["tgn2"], 1e-5, gi + 3, fps=T, part=p1)
         # alpha*(xsp + conv) + (1-alpha)*xsp = xsp + alpha*(conv + bias)            (temporal_ae.py:68-69)
         out = self.buf(name, M, rb.cout)
-        self.gemm(a4, L["tconv2"], out, taps=ops.TAPS_T3, geom=(hw, T, 1), s_acc=L["alpha"], res1=xsp)
-        return out
+        self.gemm(a4, L["tconv2"], out, taps=ops.TAPS_T3, geom=(hw, T, 1), s_acc=L["alpha"], res1=xsp, stats=pd)
+        return out, pd
 
-    def _attn(self, x, T, h, w):
-        """GN -> q,k,v (1x1) -> softmax(q k^T / sqrt(C)) v -> proj_out -> + x, one head of dim C, per frame."""
+    def _attn(self, x, T, h, w, xp=None):
+        """GN -> q,k,v (1x1) -> softmax(q k^T / sqrt(C)) v -> proj_out -> + x, one head of dim C, per frame.
+        Returns (output, its GroupNorm column partials or None)."""
         A = self.attn
         Cc, hw, M = x.shape[1], h * w, T * h * w
         assert hw % 64 == 0, "decoder attention needs h*w to be a multiple of 64"
         y = self.buf("d.attn_y", M, Cc)
-        xn = ops.groupnorm(x, self.buf("d.a1", M, Cc), T, hw, A["norm"][0], A["norm"][1], 1e-6, False,
-                           self.gn_stats[A["gn_idx"], :T], groups=self.cfg.num_groups, ws=self.gn_ws)
+        yp = self.part("d.attn_y", M, Cc) if self._fuse_stats(T, h, w) else None
+        xn = self._gn(x, self.buf("d.a1", M, Cc), T, hw, A["norm"], 1e-6, A["gn_idx"], part=xp, silu=False)
         q = self.gemm(xn, A["q"], self.buf("d.q", M, Cc))
         k = self.gemm(xn, A["k"], self.buf("d.k", M, Cc))
         o = self.buf("d.o", M, Cc)
@@ -140,8 +163,8 @@ class DecoderRuntime:
             ops.gemm(q[rows], k[rows], s, s_acc=float(Cc) ** -0.5)
             ops.softmax_rows(s, p)
             ops.gemm(p, vT, o[rows], bias=A["v_b"])
-        self.gemm(o, A["proj"], y, res1=x)
-        return y
+        self.gemm(o, A["proj"], y, res1=x, stats=yp)
+        return y, yp
 
     # ------------------------------------------------------------------ forward
     def forward(self, z_tokens: torch.Tensor, T: int, h: int, w: int, out: torch.Tensor, out_frame0: int = 0,
@@ -159,19 +182,19 @@ class DecoderRuntime:
         M = T * h * w
         x = ops.conv3x3_small_cin(z_tokens, cfg.z_channels, self.conv_in_w, self.conv_in_b,
                                   self.buf("d.in", M, self.plan.block_in), T, h, w)
-        x = self._resblock(self.res[self.plan.mid[0].prefix], x, T, h, w, "d.r0")
-        x = self._attn(x, T, h, w)
-        x = self._resblock(self.res[self.plan.mid[1].prefix], x, T, h, w, "d.r1")
+        x, xp = self._resblock(self.res[self.plan.mid[0].prefix], x, T, h, w, "d.r0")
+        x, xp = self._attn(x, T, h, w, xp)
+        x, xp = self._resblock(self.res[self.plan.mid[1].prefix], x, T, h, w, "d.r1", xp)
         for li, (blocks, up, ch) in enumerate(self.plan.levels):
             for bi, rb in enumerate(blocks):
-                x = self._resblock(self.res[rb.prefix], x, T, h, w, f"d.r{bi % 2}")
+                x, xp = self._resblock(self.res[rb.prefix], x, T, h, w, f"d.r{bi % 2}", xp)
             if up is not None:
                 xu = ops.upsample2x(x, self.buf("d.up", T * 4 * h * w, ch), T, h, w, ch)
                 h, w = 2 * h, 2 * w
-                x = self.gemm(xu, self.ups[up], self.buf("d.upc", T * h * w, ch), taps=ops.TAPS_3X3, geom=(w, h, T))
+                xp = self.part("d.upc", T * h * w, ch) if self._fuse_stats(T, h, w) else None
+                x = self.gemm(xu, self.ups[up], self.buf("d.upc", T * h * w, ch), taps=ops.TAPS_3X3, geom=(w, h, T), stats=xp)
         M = T * h * w
-        a = ops.groupnorm(x, self.buf("d.a1", M, self.plan.final_ch), T, h * w, self.norm_out[0], self.norm_out[1], 1e-6,
-                          True, self.gn_stats[self.norm_out_idx, :T], groups=cfg.num_groups, ws=self.gn_ws)
+        a = self._gn(x, self.buf("d.a1", M, self.plan.final_ch), T, h * w, self.norm_out, 1e-6, self.norm_out_idx, part=xp)
         y = self.gemm(a, self.out_conv, self.buf("d.y", M, 8, torch.float32), taps=ops.TAPS_3X3, geom=(w, h, T))
         ops.time_mix_small(y, self.tmix_w, self.tmix_b, out, blend, T, h * w, cfg.out_ch, out_frame0, skip_frames)
         return out
@@ -258,6 +281,9 @@ class EncoderRuntime(DecoderRuntime):
         self.out_conv = Lin(w8.contiguous(), b8, 32)
         self.n_moments = ow.shape[0]
 
+    def _fuse_stats(self, n, h, w) -> bool:
+        return False        # the encoder runs once per sample on one frame group: statistics keep their own pass
+
     def _enc_resblock(self, L, x, n, h, w, name):
         rb: DecResBlockSpec = L["spec"]
         hw, M, gi = h * w, n * h * w, L["gn_idx"]
@@ -288,7 +314,7 @@ class EncoderRuntime(DecoderRuntime):
                 h, w = ho, wo
                 x = self.gemm(col, self.downs[down], self.buf("e.down", n * h * w, ch))
         x = self._enc_resblock(self.res["mid.block_1"], x, n, h, w, "e.m0")
-        x = self._attn(x, n, h, w)
+        x, _ = self._attn(x, n, h, w)
         x = self._enc_resblock(self.res["mid.block_2"], x, n, h, w, "e.m1")
         M = n * h * w
         a = ops.groupnorm(x, self.buf("e.a1", M, self.mid_ch), n, h * w, self.norm_out[0], self.norm_out[1], 1e-6,
