@@ -127,6 +127,12 @@ int b200v_attention_spatial_v4(const void* q, int64_t ld_q, const void* k, int64
 int b200v_attention_spatial_v5(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                                void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
+/* Sixth generation: the v5 kernel with two softmax threads per query row (8 softmax warps per tile, 16 per CTA): each
+ * thread holds 64 scores, the halves of a row exchange their maximum through shared memory, vote on the lazy rescale
+ * tile-wide and publish their P chunks in parallel — two warps per scheduler keep the MUFU fed during a tile's turn. */
+int b200v_attention_spatial_v6(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                               void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
+
 /* Temporal self-attention over the T frames of each pixel (seq len T <= 32, head dim 64).
  * Replaces the batchified xformers call at vwm/modules/attention.py:384-399 reached from
  * vwm/modules/video_attention.py:127 and both "(b t) s c <-> (b s) t c" rearranges (:116,:140):
@@ -248,6 +254,29 @@ int b200v_time_mix_small(const float* x /* [T*HW, ldx] fp32, C channels used */,
                          const float* w /* [C,C,3] */, const float* bias,
                          float* out /* NCHW fp32 */, const int32_t* blend, int32_t T, int32_t HW, int32_t C,
                          int32_t out_frame0, int32_t skip_frames, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Callers' glue as device code (csrc/glue.cu).
+ *   time_mix_small_u8 : time_mix_small that ALSO stores every frame it produces the way the reference's output
+ *       path does — clamp((x + 1) / 2, 0, 1) (sample_utils.py:374), 255 * s truncated to uint8, "t c h w -> t h w c"
+ *       (sample_utils.py:96-126) — into out_u8 [frames, HW, C].  The fp32 NCHW `out` is only written for frames
+ *       t >= keep_f32_from (the tail a later chunk blends with; < 0 = every frame) and read for blended frames.
+ *   rollout_advance : between two rounds of the long-horizon rollout (sample_utils.py:318-365): optional
+ *       sample[0] = z0 (first round, :336), samples_z[dst_frame0 + t] = sample[t] for t >= src_frame0 (:337,:362),
+ *       filled = fill_latent(sample[-n_cond:], T, [0..n_cond-1]) (:350, :280-283; NULL = last round).
+ *   ensemble_reward : reward_utils.py:318-337 — out2[0] = mean_i var_k(member_k[i]) (unbiased over the K members,
+ *       fp32 per element as the reference, fp64 fixed-order sum), out2[1] = exp(-out2[0]).  members_dev = device
+ *       array of K device pointers; partial >= b200v_ensemble_reward_scratch() doubles; ticket = zeroed uint32
+ *       (self-resetting).
+ * ---------------------------------------------------------------------------------------------- */
+int b200v_time_mix_small_u8(const float* x, int64_t ldx, const float* w, const float* bias, float* out, uint8_t* out_u8,
+                            const int32_t* blend, int32_t T, int32_t HW, int32_t C, int32_t out_frame0,
+                            int32_t skip_frames, int32_t keep_f32_from, void* stream);
+int b200v_rollout_advance(float* sample, const float* z0, float* samples_z, float* filled, int32_t T, int64_t frame_elems,
+                          int32_t dst_frame0, int32_t src_frame0, int32_t n_cond, void* stream);
+int b200v_ensemble_reward_scratch(void);
+int b200v_ensemble_reward(const float* const* members_dev, int32_t K, int64_t n, double* partial, uint32_t* ticket,
+                          float* out2, void* stream);
 
 /* Layout converters at the boundary: NCHW fp32 <-> token-major (NHWC) fp16/fp32. */
 int b200v_nchw_to_tokens(const float* x, void* out_f16, int64_t ldo, int32_t NB, int32_t C, int32_t H, int32_t W,

@@ -7,6 +7,8 @@ that produced them; inputs are regenerated from the seed (vista_b200/synth.py) b
 """
 from __future__ import annotations
 
+import contextlib
+import io
 import os
 import sys
 import time
@@ -228,6 +230,46 @@ def gen_encoder(name):
                         weight_checksum=synth.state_dict_checksum(sd))
 
 
+def cond_embedder_inputs(cfg, h, w, n):
+    """Seeded inputs of the cond_frames embedder fixture (shared with the tests): images and the quant_conv parameters."""
+    x = synth.normal(21, "cemb.x", (n, cfg.in_channels, h, w), std=0.5)
+    qw = synth.normal(22, "cemb.qw", (2 * cfg.z_channels, 2 * cfg.z_channels, 1, 1), std=0.35)
+    qb = synth.normal(23, "cemb.qb", (2 * cfg.z_channels,), std=0.05)
+    return x, qw, qb
+
+
+def gen_cond_embedder(name="cond_embedder_tiny"):
+    """The REAL VideoPredictionEmbedderWithEncoder (encoders/modules.py:428-502) over the REAL AutoencoderKLModeOnly
+    (autoencoder.py:519-528), configured like vista.yaml:68-96 at the tiny encoder preset: n_cond_frames 1, n_copies 2,
+    is_ae, chunks of 2 frames, scale_factor 0.5 (the YAML leaves 1.0; a non-trivial value pins the multiply)."""
+    ref_loader.load_reference()
+    from vwm.modules.encoders.modules import VideoPredictionEmbedderWithEncoder
+    preset, h, w, n = "tiny", 32, 64, 3
+    cfg = spec.encoder_preset(preset)
+    sd = synth.synth_state_dict(spec.encoder_param_specs(cfg), seed=3)
+    dd = dict(ref_loader.vista_yaml()["model"]["params"]["conditioner_config"]["params"]["emb_models"][3]["params"]["encoder_config"]["params"]["ddconfig"])
+    dd.update(ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, z_channels=cfg.z_channels, in_channels=cfg.in_channels)
+    with contextlib.redirect_stdout(io.StringIO()):
+        emb = VideoPredictionEmbedderWithEncoder(
+            n_cond_frames=1, n_copies=2, is_ae=True, scale_factor=0.5, disable_encoder_autocast=True, en_and_decode_n_samples_a_time=2,
+            encoder_config={"target": "vwm.models.autoencoder.AutoencoderKLModeOnly",
+                            "params": {"embed_dim": cfg.z_channels, "monitor": "val/rec_loss", "ddconfig": dd,
+                                       "loss_config": {"target": "torch.nn.Identity"}}}).eval()
+    x, qw, qb = cond_embedder_inputs(cfg, h, w, n)
+    missing, unexpected = emb.encoder.load_state_dict(
+        {**{"encoder." + k: torch.from_numpy(v) for k, v in sd.items()}, "quant_conv.weight": torch.from_numpy(qw),
+         "quant_conv.bias": torch.from_numpy(qb)}, strict=False)
+    assert not unexpected and all(k.startswith(("decoder.", "post_quant_conv.")) for k in missing), (missing, unexpected)
+    with torch.no_grad():
+        out = emb(torch.from_numpy(x))
+        emb.skip_encode = True
+        passthrough = emb(torch.from_numpy(x))
+    assert torch.equal(passthrough, torch.from_numpy(x))
+    print(f"{name}: out {tuple(out.shape)} absmean {out.abs().mean():.4f}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), out=out.numpy(), h=h, w=w, n=n,
+                        weight_checksum=synth.state_dict_checksum(sd))
+
+
 def gen_anchors():
     """Closed-form pieces straight from the reference classes."""
     ref = ref_loader.load_reference()
@@ -276,7 +318,7 @@ def gen_full_step():
 
 def main(argv):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    cases = argv or (["anchors"] + list(UNET_CASES) + list(SAMPLER_CASES) + list(DECODER_CASES) + list(DECODE_FS_CASES) + list(ENCODER_CASES))
+    cases = argv or (["anchors"] + list(UNET_CASES) + list(SAMPLER_CASES) + list(DECODER_CASES) + list(DECODE_FS_CASES) + list(ENCODER_CASES) + ["cond_embedder_tiny"])
     for cname in cases:
         if cname == "anchors":
             gen_anchors()
@@ -292,6 +334,8 @@ def main(argv):
             gen_decode_fs(cname)
         elif cname in ENCODER_CASES:
             gen_encoder(cname)
+        elif cname == "cond_embedder_tiny":
+            gen_cond_embedder(cname)
         elif cname == "vista_full_step":
             gen_full_step()
         else:

@@ -430,3 +430,19 @@ def encode_first_stage(sd: SD, cfg, x: torch.Tensor, scale_factor=0.18215, n_sam
             z = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise[i:i + n_samples]
         outs.append(z)
     return torch.cat(outs, dim=0) * scale_factor
+
+
+def cond_frames_embed(sd: SD, quant_w: torch.Tensor, quant_b: torch.Tensor, cfg, vid: torch.Tensor, scale_factor: float = 1.0,
+                      n_cond_frames: int = 1, n_copies: int = 1, n_samples: Optional[int] = None) -> torch.Tensor:
+    """VideoPredictionEmbedderWithEncoder.forward without noise augmentation (encoders/modules.py:462-502) over
+    AutoencoderKLModeOnly.encode (autoencoder.py:467-488,519-528): moments = quant_conv(Encoder(x)), the regulariser in
+    mode (sample=False) keeps the mean half; chunks of n_samples; * scale_factor; "(b t) c h w -> b (t c) h w"; n_copies."""
+    n_samples = vid.shape[0] if n_samples is None else n_samples
+    outs = []
+    for i in range(0, vid.shape[0], n_samples):
+        mom = F.conv2d(encoder_forward(sd, cfg, vid[i:i + n_samples]), quant_w, quant_b)
+        outs.append(torch.chunk(mom, 2, dim=1)[0])
+    out = torch.cat(outs, dim=0) * scale_factor
+    bt, c, h, w = out.shape
+    out = out.reshape(bt // n_cond_frames, n_cond_frames * c, h, w)
+    return out.repeat_interleave(n_copies, dim=0)

@@ -168,6 +168,39 @@ def time_mix_small(x, w, bias, out, blend, T, HW, Cc, out_frame0=0, skip_frames=
     return out
 
 
+def time_mix_small_u8(x, w, bias, out, out_u8, blend, T, HW, Cc, out_frame0=0, skip_frames=0, keep_f32_from=-1):
+    tmp = out.clone()
+    time_mix_small(x, w, bias, tmp, blend, T, HW, Cc, out_frame0, skip_frames)
+    for t in range(skip_frames, T):
+        f = out_frame0 + t
+        s = ((tmp[f] + 1.0) / 2.0).clamp(0.0, 1.0)
+        out_u8[f] = (255.0 * s).to(torch.uint8).permute(1, 2, 0)          # float -> uint8 truncates, like numpy astype
+        if keep_f32_from < 0 or t >= keep_f32_from:
+            out[f] = tmp[f]
+    return out_u8
+
+
+def rollout_advance(sample, z0, samples_z, filled, dst_frame0, src_frame0, n_cond):
+    T = sample.shape[0]
+    if z0 is not None:
+        sample[0] = z0[0]
+    samples_z[dst_frame0 + src_frame0:dst_frame0 + T] = sample[src_frame0:]
+    if filled is not None:
+        filled.zero_()
+        filled[:n_cond] = sample[T - n_cond:]
+    return samples_z
+
+
+def ensemble_reward(members):
+    K = len(members)
+    u = torch.mean(torch.stack(members), 0)
+    diff = torch.zeros_like(members[0])
+    for m in members:
+        diff.add_((m - u) ** 2)
+    mv = (diff / (K - 1)).double().mean().float()
+    return torch.stack([mv, torch.exp(-mv)])
+
+
 def groupnorm_sums(x, frames, tokens_per_frame, Cc, sums, frames_per_stat, groups=32, ws=None):
     xs = x[:, :Cc].double().reshape(frames // frames_per_stat, frames_per_stat * tokens_per_frame, groups, Cc // groups)
     sums.copy_(torch.stack([xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))], dim=-1).reshape(sums.shape))
@@ -292,8 +325,8 @@ _PATCHED = ["gemm", "GNWorkspace", "groupnorm_scratch", "groupnorm", "conv3x3_sm
             "softmax_rows", "nchw_to_tokens", "tokens_to_nchw", "time_mix_small", "groupnorm_sums",
             "groupnorm_finalize_apply", "groupnorm_from_partials", "groupnorm_apply", "layernorm", "attention_spatial", "attention_temporal",
             "attention_temporal_sharded", "timestep_embedding", "blend_emb", "im2col_s2", "sampler_prepare",
-            "sampler_update"]
-_NOT_TAPED = {"GNWorkspace", "groupnorm_scratch"}
+            "sampler_update", "time_mix_small_u8", "rollout_advance", "ensemble_reward"]
+_NOT_TAPED = {"GNWorkspace", "groupnorm_scratch", "rollout_advance", "ensemble_reward"}
 
 
 @contextlib.contextmanager

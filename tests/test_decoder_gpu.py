@@ -94,3 +94,16 @@ def test_encoder_matches_reference(name, preset, h, w, n):
     r = rel_l2(z.cpu(), torch.from_numpy(g["z"]))
     print(f"{name}: encode_first_stage rel-L2 {r:.3e}")
     assert r < 5e-3, r
+
+
+def test_cond_frames_embedder_matches_reference():
+    """conditioner.VideoPredictionEmbedderWithEncoder on the GPU (quant_conv folded into the encoder's conv_out) against the
+    fixture from the REAL embedder + AutoencoderKLModeOnly (encoders/modules.py:428-502, autoencoder.py:519-528)."""
+    from test_executor_cpu import _cond_embedder
+    emb, x = _cond_embedder(DEV)
+    out = emb(x)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(golden("cond_embedder_tiny")["out"])
+    r = rel_l2(out.cpu(), ref)
+    print(f"cond_frames embedder: rel-L2 {r:.3e}")
+    assert out.shape == ref.shape and r < 5e-3, r

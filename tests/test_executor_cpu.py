@@ -395,3 +395,154 @@ def test_engine_encode_sample_decode_on_emulated_ops(monkeypatch):
         frames_ref = vo.decode_first_stage(to_t(dsd), dcfg, lat_ref)
     assert rel_l2(z, z_ref) < 5e-3 and rel_l2(lat, lat_ref) < 5e-3 and rel_l2(frames, frames_ref) < 1e-2
     assert frames.shape == (T, 3, 2 * h, 2 * w)
+
+
+def _tiny_engine(monkeypatch, steps=3, guider=None):
+    """configs/inference/vista_b200.yaml at tiny sizes on CPU executors over the emulated operators."""
+    import os
+    import yaml
+    from helpers import decoder_weights, unet_weights
+    from vista_b200 import fused as fused_mod
+    from vista_b200 import vae as vae_mod
+    from vista_b200.diffusion import instantiate_from_config
+    monkeypatch.setattr(fused_mod, "USE_GRAPH", False)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, "configs", "inference", "vista_b200.yaml")))["model"]
+    p = cfg["params"]
+    p["network_config"]["params"].update(model_channels=64, channel_mult=[1, 2], num_res_blocks=1, attention_resolutions=[1, 2])
+    p["first_stage_config"]["params"]["decoder_config"]["params"].update(ch=64, ch_mult=[1, 2], num_res_blocks=1)
+    p["sampler_config"]["params"].update(num_steps=steps, device="cpu")
+    if guider is not None:
+        p["sampler_config"]["params"]["guider_config"] = guider
+    p["replace_cond_frames"], p["fixed_cond_frames"] = True, [0]
+    p["en_and_decode_n_samples_a_time"] = 14
+    eng = instantiate_from_config(cfg)
+    ucfg, usd = unet_weights("tiny")
+    dcfg, dsd = decoder_weights("tiny")
+    sd = {"model.diffusion_model." + k: torch.from_numpy(v) for k, v in usd.items()}
+    sd.update({"first_stage_model.decoder." + k: torch.from_numpy(v) for k, v in dsd.items()})
+    missing, unexpected = eng.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    eng.model._require_cuda = eng.model.diffusion_model._require_cuda = lambda device: None
+    monkeypatch.setattr(vae_mod.VideoDecoder, "runtime", lambda self, device: self.__dict__.setdefault(
+        "_rt_cpu", vae_mod.DecoderRuntime(self.b200_config, self.state_dict(), "cpu")))
+    return eng, (ucfg, usd), (dcfg, dsd)
+
+
+def _reference_rollout(sample_fn, c, z, noises, T, scale_factor, n_cond=3):
+    """sample_utils.py:318-365 restated with the conditioner reduced to what the hot path sees: between rounds
+    c["concat"] = sample[[-3]] / scale_factor (:343 through the skip_encode embedder, encoders/modules.py:470-471)."""
+    init_mask, pred_mask = torch.zeros(T), torch.zeros(T)
+    init_mask[0] = 1
+    pred_mask[list(range(n_cond))] = 1
+    rounds = len(noises)
+    samples_z = torch.zeros((rounds * (T - n_cond) + n_cond,) + tuple(z.shape[1:]))
+    sample = sample_fn(noises[0].clone(), c, z, init_mask)
+    sample[0] = z[0]
+    samples_z[:T] = sample
+    for n in range(rounds - 1):
+        c = dict(c)
+        c["concat"] = (sample[[-n_cond]] / scale_factor).expand(c["concat"].shape[0], -1, -1, -1).contiguous()
+        filled = torch.zeros_like(z)
+        filled[list(range(n_cond))] = sample[-n_cond:]
+        sample = sample_fn(noises[n + 1].clone(), c, filled, pred_mask)
+        samples_z[(n + 1) * (T - n_cond) + n_cond:(n + 1) * (T - n_cond) + T] = sample[n_cond:]
+    return samples_z
+
+
+def test_engine_rollout_u8_and_ensemble_on_emulated_ops(monkeypatch):
+    """SURVEY 8f rows 2-4 on emulated operators: engine.rollout (3 rounds, TrianglePredictionGuider, concat re-conditioning)
+    against the same loop over the CPU oracle; the fused uint8 NHWC output against the reference's clamp / scale /
+    truncate / rearrange of the fp32 frames; engine.sample_ensemble against reward_utils.py:318-337 over the oracle."""
+    from oracle import vista_oracle as vo
+    T, h, w, steps, rounds = 25, 8, 16, 2, 3
+    guider = {"target": "vista_b200.diffusion.TrianglePredictionGuider", "params": {"max_scale": 2.5, "num_frames": T}}
+    eng, (ucfg, usd), (dcfg, dsd) = _tiny_engine(monkeypatch, steps=steps, guider=guider)
+    c, uc = synth.synth_conditioning(7, T, h, w, trajectory=True, context_dim=ucfg.context_dim, adm=ucfg.adm_in_channels)
+    _, z, _ = synth.synth_latents(7, T, h, w)
+    td = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    zt = torch.from_numpy(z)
+    noises = [torch.from_numpy(synth.normal(40 + i, "rollout.noise", (T, 4, h, w), std=1.0)) for i in range(rounds)]
+    with patched_ops(), torch.no_grad():
+        frames, samples_z = eng.rollout(td(c), td(uc), zt, rounds, noises=noises)
+        frames8, samples_z8 = eng.rollout(td(c), td(uc), zt, rounds, noises=noises, u8=True)
+    n_out = rounds * (T - 3) + 3
+    assert samples_z.shape == (n_out, 4, h, w) and frames.shape == (n_out, 3, 2 * h, 2 * w)
+    assert frames8.shape == (n_out, 2 * h, 2 * w, 3) and frames8.dtype == torch.uint8
+    assert torch.equal(samples_z, samples_z8)
+    # reference output path (sample_utils.py:374 then :96-126) applied to OUR fp32 frames: must be the same bytes
+    want8 = (255.0 * frames).to(torch.uint8).permute(0, 2, 3, 1)
+    assert torch.equal(frames8, want8)
+    sdt = to_t(usd)
+    with torch.no_grad():
+        ref_z = _reference_rollout(lambda nz, cc, cf, m: vo.euler_edm_sample(sdt, ucfg, nz, cc, td(uc), cf, m, steps, T,
+                                                                           guider="TrianglePredictionGuider", scale=2.5),
+                                   td(c), zt, noises, T, eng.scale_factor)
+        ref_x = vo.decode_first_stage(to_t(dsd), dcfg, ref_z)
+        ref_frames = torch.clamp((ref_x + 1.0) / 2.0, 0.0, 1.0)
+    assert rel_l2(samples_z, ref_z) < 5e-3, rel_l2(samples_z, ref_z)
+    assert rel_l2(frames, ref_frames) < 1e-2
+    ref8 = (255.0 * ref_frames).to(torch.uint8).permute(0, 2, 3, 1)
+    assert (frames8.int() - ref8.int()).abs().max() <= 3 and (frames8 != ref8).float().mean() < 0.25
+
+    # ensemble reward (VanillaCFG like reward_utils / sample.py's single-round default)
+    eng2, (ucfg, usd), _ = _tiny_engine(monkeypatch, steps=steps)
+    K = 3
+    en = [torch.from_numpy(synth.normal(60 + i, "ens.noise", (T, 4, h, w), std=1.0)) for i in range(K)]
+    with patched_ops(), torch.no_grad():
+        reward, members = eng2.sample_ensemble(td(c), td(uc), zt, K, noises=en)
+    mask = torch.zeros(T)
+    mask[0] = 1
+    with torch.no_grad():
+        ref_members = []
+        for i in range(K):
+            s = vo.euler_edm_sample(sdt, ucfg, en[i].clone(), td(c), td(uc), zt, mask, steps, T)
+            s[0] = zt[0]
+            ref_members.append(s)
+        u = torch.mean(torch.stack(ref_members), 0)
+        diff = torch.zeros_like(u)
+        for s in ref_members:
+            diff.add_((s - u) ** 2)
+        ref_reward = torch.exp(-(diff / (K - 1)).mean())
+    assert all(rel_l2(a, b) < 5e-3 for a, b in zip(members, ref_members))
+    assert abs(float(reward) - float(ref_reward)) < 2e-3 * max(1.0, abs(float(ref_reward))), (float(reward), float(ref_reward))
+
+
+def _cond_embedder(device="cpu"):
+    """vista_b200.conditioner.VideoPredictionEmbedderWithEncoder built from the reference's own YAML shape
+    (vista.yaml:68-96 with the two `target:` strings changed), loaded through the reference checkpoint key layout."""
+    from oracle.make_golden import cond_embedder_inputs
+    from vista_b200.conditioner import VideoPredictionEmbedderWithEncoder
+    cfg = spec.encoder_preset("tiny")
+    sd = synth.synth_state_dict(spec.encoder_param_specs(cfg), seed=3)
+    dd = dict(attn_type="vanilla-xformers", double_z=True, z_channels=cfg.z_channels, resolution=256, in_channels=cfg.in_channels,
+              out_ch=3, ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, attn_resolutions=[], dropout=0.0)
+    emb = VideoPredictionEmbedderWithEncoder(
+        n_cond_frames=1, n_copies=2, is_ae=True, scale_factor=0.5, disable_encoder_autocast=True, en_and_decode_n_samples_a_time=2,
+        encoder_config={"target": "vista_b200.conditioner.AutoencoderKLModeOnly",
+                        "params": {"embed_dim": cfg.z_channels, "monitor": "val/rec_loss", "ddconfig": dd,
+                                   "loss_config": {"target": "torch.nn.Identity"}}})
+    x, qw, qb = cond_embedder_inputs(cfg, 32, 64, 3)
+    ck = {"encoder.encoder." + k: torch.from_numpy(v) for k, v in sd.items()}
+    ck.update({"encoder.quant_conv.weight": torch.from_numpy(qw), "encoder.quant_conv.bias": torch.from_numpy(qb),
+               "encoder.decoder.conv_in.weight": torch.zeros(1), "encoder.post_quant_conv.weight": torch.zeros(1)})
+    missing, unexpected = emb.load_state_dict(ck, strict=False)          # sample_utils.py:72 loads with strict=False
+    assert not missing and sorted(unexpected) == ["encoder.decoder.conv_in.weight", "encoder.post_quant_conv.weight"]
+    return emb.to(device), torch.from_numpy(x).to(device)
+
+
+def test_cond_frames_embedder_on_emulated_ops_matches_reference(monkeypatch):
+    from helpers import golden
+    from vista_b200 import conditioner as cmod
+    from vista_b200 import vae as vae_mod
+    emb, x = _cond_embedder()
+    monkeypatch.setattr(cmod.AutoencoderKLModeOnly, "runtime", lambda self, device: self.__dict__.setdefault(
+        "_rt_cpu", vae_mod.EncoderRuntime(self.encoder.b200_config, self.encoder.state_dict(), "cpu",
+                                          post=(self.get_parameter("quant_conv.weight").detach().float().flatten(1),
+                                                self.get_parameter("quant_conv.bias").detach().float()))))
+    with patched_ops(), torch.no_grad():
+        out = emb(x)
+        emb.skip_encode = True
+        assert emb(x) is x                         # latents pass through (encoders/modules.py:470-471)
+    ref = torch.from_numpy(golden("cond_embedder_tiny")["out"])
+    assert out.shape == ref.shape and rel_l2(out, ref) < 5e-3, rel_l2(out, ref)

@@ -166,3 +166,19 @@ def test_encoder_param_inventory():
     # 34.2 M parameters
     e = spec.encoder_param_specs(spec.encoder_preset("vista"))
     assert len(e) == 106 and sum(int(np.prod(v[0])) for v in e.values()) == 34163592
+
+
+def test_cond_frames_embedder_oracle_matches_reference():
+    """oracle.cond_frames_embed against the REAL VideoPredictionEmbedderWithEncoder over the REAL AutoencoderKLModeOnly
+    (oracle/make_golden.py:gen_cond_embedder; encoders/modules.py:428-502, autoencoder.py:519-528)."""
+    from oracle.make_golden import cond_embedder_inputs
+    g = golden("cond_embedder_tiny")
+    cfg = spec.encoder_preset("tiny")
+    sd = synth.synth_state_dict(spec.encoder_param_specs(cfg), seed=3)
+    assert synth.state_dict_checksum(sd) == str(g["weight_checksum"])
+    x, qw, qb = cond_embedder_inputs(cfg, int(g["h"]), int(g["w"]), int(g["n"]))
+    with torch.no_grad():
+        out = vo.cond_frames_embed(to_t(sd), torch.from_numpy(qw), torch.from_numpy(qb), cfg, torch.from_numpy(x),
+                                   scale_factor=0.5, n_cond_frames=1, n_copies=2, n_samples=2)
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape and rel_l2(out, ref) < 2e-5, rel_l2(out, ref)

@@ -327,6 +327,95 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict
   }
 }
 
+// LayerNorm for C = 40 * LPR (320 / 640 / 1280: LPR = 8 / 16 / 32 lanes per row, every lane 5 16-byte vectors, no idle
+// lanes; a warp normalises 32 / LPR rows per iteration).  gamma / beta live in registers for the whole grid-stride loop
+// (the one-warp-per-token kernel re-read them from L1 for every token: 128 of its 160 load sectors per token and a third
+// of its instructions), the next rows are prefetched while the current ones are reduced: an HBM stream.
+template <int LPR>
+__global__ void __launch_bounds__(128, 3)
+layernorm40_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, long long tokens,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   const float* __restrict__ addvec, long long ld_addvec, int av_div, int av_mod) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int C = LPR * 40;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rowi = lane / LPR;
+  float g[5][8], b[5][8];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int c0 = (sub + j * LPR) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    g[j][0] = g0.x; g[j][1] = g0.y; g[j][2] = g0.z; g[j][3] = g0.w; g[j][4] = g1.x; g[j][5] = g1.y; g[j][6] = g1.z; g[j][7] = g1.w;
+    b[j][0] = b0.x; b[j][1] = b0.y; b[j][2] = b0.z; b[j][3] = b0.w; b[j][4] = b1.x; b[j][5] = b1.y; b[j][6] = b1.z; b[j][7] = b1.w;
+  }
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  long long token = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + rowi;
+  const long long stride = n_warps * RPW;
+  uint4 raw[5];
+  if (token < tokens) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) raw[j] = __ldg(reinterpret_cast<const uint4*>(x + token * ldx + (sub + j * LPR) * 8));
+  }
+  // every lane of a warp runs the same number of iterations (the shuffles need the whole warp): loop on the warp's first row
+  for (long long base = token - rowi; base < tokens; base += stride, token += stride) {
+    const long long next = token + stride;
+    uint4 nxt[5];
+    if (next < tokens) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) nxt[j] = __ldg(reinterpret_cast<const uint4*>(x + next * ldx + (sub + j * LPR) * 8));
+    }
+    const bool live = token < tokens;
+    float v[5][8];
+    float sum = 0.f;
+    if (live) {
+      const float* av = addvec ? addvec + ((token / av_div) % av_mod) * ld_addvec : nullptr;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        h8_to_f(raw[j], v[j]);
+        if (av) {
+          const int c0 = (sub + j * LPR) * 8;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + c0)), a1 = __ldg(reinterpret_cast<const float4*>(av + c0 + 4));
+          v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
+          v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += v[j][i];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+    }
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[j][i] -= mean;
+        sq = fmaf(v[j][i], v[j][i], sq);
+      }
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(v[j][i] * rstd, g[j][i], b[j][i]);
+        *reinterpret_cast<uint4*>(y + token * ldy + (sub + j * LPR) * 8) = f_to_h8(o);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) raw[j] = nxt[j];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Temporal attention: sequence = the T <= 32 frames of one pixel, head dim 64.  One warp per
 // (clip, pixel, head): q/k/v rows (128 B each, strided over frames) are brought to shared memory with
@@ -967,6 +1056,29 @@ extern "C" int b200v_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy,
   const long long blocks_needed = (tokens + wpb - 1) / wpb;
   const int nv = (C / 8 + 31) / 32;
   const int ad = av_div > 0 ? av_div : 1, am = av_mod > 0 ? av_mod : 1;
+  static const bool ln40 = !(getenv("VB_LN40") && atoi(getenv("VB_LN40")) == 0);
+  if (ln40 && (C == 320 || C == 640 || C == 1280)) {
+    // the UNet's three widths: lanes-per-row kernel (gamma / beta in registers, no idle lanes)
+    using namespace vb;
+#define VB_LN40_LAUNCH(LPR)                                                                                          \
+  {                                                                                                                  \
+    static int per_sm = 0;                                                                                           \
+    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm40_kernel<LPR>, 128, 0) !=   \
+                            cudaSuccess || per_sm <= 0))                                                            \
+      per_sm = 3;                                                                                                    \
+    const long long need = (tokens + 4 * (32 / LPR) - 1) / (4 * (32 / LPR));                                         \
+    long long blocks = (long long)device_sm_count() * per_sm;                                                        \
+    if (blocks > need) blocks = need;                                                                                \
+    layernorm40_kernel<LPR><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(                                     \
+        (const __half*)x, ldx, (__half*)y, ldy, tokens, gamma, beta, eps, addvec, ld_addvec, ad, am);                \
+  }
+    if (C == 320) VB_LN40_LAUNCH(8)
+    else if (C == 640) VB_LN40_LAUNCH(16)
+    else VB_LN40_LAUNCH(32)
+#undef VB_LN40_LAUNCH
+    VB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   // one resident wave of blocks (occupancy by register count), the warps stride over the tokens
 #define VB_LN_LAUNCH(NV)                                                                                             \
   {                                                                                                                  \

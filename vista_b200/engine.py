@@ -123,6 +123,17 @@ class DiffusionEngine(nn.Module):
         return _decode_first_stage(dec.runtime(z.device), z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap)
 
     @torch.no_grad()
+    def decode_first_stage_u8(self, z: torch.Tensor, overlap: int = 3) -> torch.Tensor:
+        """Extension: the decoded frames as (F, H, W, 3) uint8 — bit for bit what the reference's
+        output path (sample_utils.py:374 clamp, :96-126 scaling / truncation / "t h w c") makes of decode_first_stage's
+        result, produced by the decoder's last kernel instead of three full-resolution fp32 passes on the host."""
+        dec = self.first_stage_model.decoder
+        if not isinstance(dec, VideoDecoder):
+            raise NotImplementedError("decode_first_stage_u8 needs vista_b200.vae.VideoDecoder as decoder_config.target")
+        return _decode_first_stage(dec.runtime(z.device), z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap,
+                                   u8=True)
+
+    @torch.no_grad()
     def encode_first_stage(self, x, noise: Optional[torch.Tensor] = None, sample: bool = True):
         """diffusion.py:183-195.  Needs ``encoder_config`` (experimental B200 encoder).  The reference samples the
         posterior with device RNG (DiagonalGaussianRegularizer, sample=True): pass ``noise`` for a reproducible draw,
@@ -152,3 +163,14 @@ class DiffusionEngine(nn.Module):
             cond_mask = cond_mask.reshape(-1)
         denoiser = B200Denoiser(self.denoiser, self.model)
         return self.sampler(denoiser, randn, cond, uc=uc, cond_frame=cond_frame, cond_mask=cond_mask)
+
+    # ---- the callers' loops as engine operations (vista_b200/rollout.py) ----
+    def rollout(self, cond: Dict, uc: Dict, z: torch.Tensor, num_rounds: int, **kwargs):
+        """Long-horizon rollout, the body of sample_utils.do_sample (sample_utils.py:318-373) -> (frames, samples_z)."""
+        from .rollout import rollout
+        return rollout(self, cond, uc, z, num_rounds, **kwargs)
+
+    def sample_ensemble(self, cond: Dict, uc: Dict, z: torch.Tensor, ensemble_size: int = 5, **kwargs):
+        """The reward path (reward_utils.py:318-337) -> (reward, members)."""
+        from .rollout import sample_ensemble
+        return sample_ensemble(self, cond, uc, z, ensemble_size, **kwargs)

@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvista_b200.so")
-SOURCES = ["host.cu", "gemm_tc.cu", "attn_tc.cu", "attn2_tc.cu", "attn5_tc.cu", "misc.cu", "mma_probe.cu"]
+SOURCES = ["host.cu", "gemm_tc.cu", "attn_tc.cu", "attn2_tc.cu", "attn5_tc.cu", "attn6_tc.cu", "misc.cu", "glue.cu", "mma_probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -99,6 +99,7 @@ SIGNATURES = {
     "b200v_attention_spatial_v3": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v4": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v5": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
+    "b200v_attention_spatial_v6": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_groupnorm_from_partials": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P],
     "b200v_groupnorm_chunk": [],
@@ -121,6 +122,10 @@ SIGNATURES = {
     "b200v_sampler_update": [_P, _P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "b200v_softmax_rows": [_P, _I64, _P, _I64, _I64, _I32, _P],
     "b200v_time_mix_small": [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P],
+    "b200v_time_mix_small_u8": [_P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    "b200v_rollout_advance": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P],
+    "b200v_ensemble_reward_scratch": [],
+    "b200v_ensemble_reward": [_P, _I32, _I64, _P, _P, _P, _P],
     "b200v_nchw_to_tokens": [_P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_tokens_to_nchw": [_P, _I32, _I64, _P, _I32, _I32, _I32, _I32, _P],
 }
@@ -133,6 +138,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib if _tape is None else _Recorder(_lib)
+    if os.path.isfile(LIB_PATH) and _stale() and os.environ.get("VISTA_B200_NO_AUTOBUILD") != "1":
+        try:                      # sources newer than the library (an edit without a rebuild): rebuild before dlopen
+            build()
+        except Exception as e:    # no nvcc on this host: the symbol check below reports what is missing
+            sys.stderr.write(f"vista_b200: stale library and rebuild failed: {e}\n")
     if not os.path.isfile(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no fallback path)")
@@ -155,7 +165,7 @@ def load() -> C.CDLL:
 # graph is not (the frame-sharded step with its NCCL calls); the same stability rules as for graph capture apply.
 # ---------------------------------------------------------------------------------------------------------------
 _tape: Optional[list] = None
-_NO_TAPE = {"b200v_groupnorm_chunk", "b200v_groupnorm_chunk_for", "b200v_version", "b200v_device_info", "b200v_last_error"}
+_NO_TAPE = {"b200v_ensemble_reward_scratch", "b200v_groupnorm_chunk", "b200v_groupnorm_chunk_for", "b200v_version", "b200v_device_info", "b200v_last_error"}
 
 
 class _Recorder:

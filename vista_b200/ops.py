@@ -201,7 +201,7 @@ ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "0"))
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
     l = _lib.load()
     fn = {1: l.b200v_attention_spatial, 2: l.b200v_attention_spatial_v2, 3: l.b200v_attention_spatial_v3,
-          4: l.b200v_attention_spatial_v4, 5: l.b200v_attention_spatial_v5}[impl or ATTN_IMPL or (5 if seq >= 2048 else 3)]
+          4: l.b200v_attention_spatial_v4, 5: l.b200v_attention_spatial_v5, 6: l.b200v_attention_spatial_v6}[impl or ATTN_IMPL or (5 if seq >= 2048 else 3)]
     _count(1)
     _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
                 2.0 * 4 * frames * seq * heads * 64)
@@ -483,4 +483,50 @@ def time_mix_small(x, w, bias, out, blend, T, HW, Cc, out_frame0=0, skip_frames=
     _lib.check(_lib.load().b200v_time_mix_small(x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(blend),
                                                 T, HW, Cc, out_frame0, skip_frames, _stream()), "b200v_time_mix_small")
     _prof_end()
+    return out
+
+
+def time_mix_small_u8(x, w, bias, out, out_u8, blend, T, HW, Cc, out_frame0=0, skip_frames=0, keep_f32_from=-1):
+    """time_mix_small that also writes the uint8 NHWC frames of the reference's output path (sample_utils.py:96-126,374)."""
+    assert out_u8.dtype == torch.uint8 and out_u8.is_contiguous()
+    _count(1)
+    _prof_begin("other", "time_mix_small_u8", 0.0, 0.0)
+    _lib.check(_lib.load().b200v_time_mix_small_u8(x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(bias), out.data_ptr(),
+                                                   out_u8.data_ptr(), _ptr(blend), T, HW, Cc, out_frame0, skip_frames,
+                                                   keep_f32_from, _stream()), "b200v_time_mix_small_u8")
+    _prof_end()
+    return out_u8
+
+
+def rollout_advance(sample, z0, samples_z, filled, dst_frame0: int, src_frame0: int, n_cond: int):
+    """sample_utils.py:335-337,350,362 as one launch (see include/vista_b200.h)."""
+    T = sample.shape[0]
+    E = sample[0].numel()
+    assert sample.is_contiguous() and samples_z.is_contiguous() and sample.dtype == torch.float32
+    assert filled is None or (filled.is_contiguous() and filled.shape == sample.shape)
+    assert samples_z.shape[0] >= dst_frame0 + T
+    _count(1)
+    _lib.check(_lib.load().b200v_rollout_advance(sample.data_ptr(), _ptr(z0), samples_z.data_ptr(), _ptr(filled), T, E,
+                                                 dst_frame0, src_frame0, n_cond, _stream()), "b200v_rollout_advance")
+    return samples_z
+
+
+_reward_ws = {}
+
+
+def ensemble_reward(members: Sequence[torch.Tensor]) -> torch.Tensor:
+    """[mean variance, reward = exp(-mean variance)] of an ensemble of equally shaped fp32 samples (reward_utils.py:327-333)."""
+    K, n, dev = len(members), members[0].numel(), members[0].device
+    assert all(m.is_contiguous() and m.dtype == torch.float32 and m.numel() == n for m in members)
+    l = _lib.load()
+    ws = _reward_ws.get(dev)
+    if ws is None:
+        ws = _reward_ws[dev] = (torch.empty(l.b200v_ensemble_reward_scratch(), dtype=torch.float64, device=dev),
+                                torch.zeros(1, dtype=torch.int32, device=dev))
+    ptrs = torch.tensor([m.data_ptr() for m in members], dtype=torch.int64).to(dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    _count(1)
+    _lib.check(l.b200v_ensemble_reward(ptrs.data_ptr(), K, n, ws[0].data_ptr(), ws[1].data_ptr(), out.data_ptr(), _stream()),
+               "b200v_ensemble_reward")
+    out._keepalive = (ptrs, tuple(members))      # the launch is asynchronous
     return out

@@ -168,9 +168,12 @@ class DecoderRuntime:
 
     # ------------------------------------------------------------------ forward
     def forward(self, z_tokens: torch.Tensor, T: int, h: int, w: int, out: torch.Tensor, out_frame0: int = 0,
-                blend: Optional[torch.Tensor] = None, skip_frames: int = 0) -> torch.Tensor:
+                blend: Optional[torch.Tensor] = None, skip_frames: int = 0, out_u8: Optional[torch.Tensor] = None,
+                keep_f32_from: int = -1) -> torch.Tensor:
         """z_tokens: [(T h w), 8] fp16 (channels >= z_channels zero).  Writes frames
-        out[out_frame0 + skip_frames : out_frame0 + T] (NCHW fp32, (n,3,8h,8w))."""
+        out[out_frame0 + skip_frames : out_frame0 + T] (NCHW fp32, (n,3,8h,8w)).  With ``out_u8`` ((F,8h,8w,3) uint8) the
+        last kernel also stores the frames as the reference's output path does (ops.time_mix_small_u8) and keeps fp32 only
+        for frames >= keep_f32_from of this call."""
         cfg = self.cfg
         if not hasattr(self, "gn_stats") or self.gn_stats.shape[1] < T:
             self._bufs.setdefault(("gn.retired",), []).append(getattr(self, "gn_stats", None))   # tapes may still point at it
@@ -196,18 +199,40 @@ class DecoderRuntime:
         M = T * h * w
         a = self._gn(x, self.buf("d.a1", M, self.plan.final_ch), T, h * w, self.norm_out, 1e-6, self.norm_out_idx, part=xp)
         y = self.gemm(a, self.out_conv, self.buf("d.y", M, 8, torch.float32), taps=ops.TAPS_3X3, geom=(w, h, T))
-        ops.time_mix_small(y, self.tmix_w, self.tmix_b, out, blend, T, h * w, cfg.out_ch, out_frame0, skip_frames)
+        if out_u8 is not None:
+            ops.time_mix_small_u8(y, self.tmix_w, self.tmix_b, out, out_u8, blend, T, h * w, cfg.out_ch, out_frame0,
+                                  skip_frames, keep_f32_from)
+        else:
+            ops.time_mix_small(y, self.tmix_w, self.tmix_b, out, blend, T, h * w, cfg.out_ch, out_frame0, skip_frames)
         return out
 
 
 def decode_first_stage(rt: DecoderRuntime, z: torch.Tensor, scale_factor: float = 0.18215, n_samples: Optional[int] = 14,
-                       overlap: int = 3) -> torch.Tensor:
-    """vwm/models/diffusion.py:150-180 on the B200 decoder.  z: (F,4,h,w) fp32 -> (F,3,8h,8w) fp32."""
+                       overlap: int = 3, u8: bool = False) -> torch.Tensor:
+    """vwm/models/diffusion.py:150-180 on the B200 decoder.  z: (F,4,h,w) fp32 -> (F,3,8h,8w) fp32.
+    ``u8``: return (F,8h,8w,3) uint8 instead — what do_sample's clamp((x+1)/2,0,1) (sample_utils.py:374) followed by
+    perform_save_locally's (255*sample).astype(uint8) in "t h w c" order (sample_utils.py:96-126) makes of the same
+    frames, written by the decoder's last kernel (no fp32 frame tensor, 4x less D2H)."""
     F_, zc, h, w = z.shape
     n_samples = F_ if n_samples is None else n_samples
     up = 2 ** (len(rt.cfg.ch_mult) - 1)
     out = torch.empty(F_, rt.cfg.out_ch, h * up, w * up, dtype=torch.float32, device=z.device)
     zs = (z.float() / scale_factor).contiguous()
+    if u8:
+        out8 = torch.empty(F_, h * up, w * up, rt.cfg.out_ch, dtype=torch.uint8, device=z.device)
+        chunks = _decode_chunks(F_, n_samples, overlap)
+        for ci, (f0, n, o0, nov) in enumerate(chunks):
+            tok = rt.buf("d.z", n * h * w, 8)
+            tok.zero_()
+            ops.nchw_to_tokens(zs[f0:f0 + n].contiguous(), tok, n, zc, h, w)
+            blend = None
+            if nov:
+                blend = torch.zeros(n, dtype=torch.int32, device=z.device)
+                blend[:nov] = 1
+            # fp32 is kept only for the frames the NEXT chunk averages with (its first `nov` output frames)
+            keep = n if ci + 1 == len(chunks) else max(0, chunks[ci + 1][2] - o0)
+            rt.forward(tok, n, h, w, out, out_frame0=o0, blend=blend, out_u8=out8, keep_f32_from=keep)
+        return out8
 
     def run(frames: torch.Tensor, out_frame0: int, n_overlap: int):
         T = frames.shape[0]
@@ -235,9 +260,12 @@ class EncoderRuntime(DecoderRuntime):
     """``Encoder.forward`` (vwm/modules/diffusionmodules/model.py:527-557): conv_in, per level ResnetBlocks
     (model.py:116-135, temb = None) + Downsample (model.py:69-83), mid (res, attn, res), GN, swish, conv_out."""
 
-    def __init__(self, cfg, sd: Dict[str, torch.Tensor], device):
+    def __init__(self, cfg, sd: Dict[str, torch.Tensor], device, post=None):
+        """post = (W [o, 2 z_channels], b [o]) fp32: a 1x1 convolution after conv_out (AutoencodingEngineLegacy.quant_conv,
+        autoencoder.py:449-453,472), folded into conv_out's weights at packing time."""
         from .spec import build_encoder_plan
         self.cfg, self.dev = cfg, torch.device(device)
+        self._post = post
         self.levels, self.mid_ch = build_encoder_plan(cfg)
         self._bufs = {}
         self._sd = sd
@@ -273,11 +301,15 @@ class EncoderRuntime(DecoderRuntime):
         self.norm_out_idx = self.n_gn
         self.n_gn += 1
         ow = conv_weight_to_taps(self._f32("conv_out.weight"))          # 2 z_channels = 8 output channels
+        ob = self._f32("conv_out.bias")
+        if getattr(self, "_post", None) is not None:                    # quant_conv o conv_out, composed in fp32
+            pw, pb = (t.to(self.dev, torch.float32) for t in self._post)
+            ow, ob = pw @ ow, pw @ ob + pb
         assert ow.shape[0] <= 8
         w8 = torch.zeros(8, ow.shape[1], dtype=torch.float16, device=self.dev)
         w8[: ow.shape[0]] = ow.to(torch.float16)
         b8 = torch.zeros(8, dtype=torch.float32, device=self.dev)
-        b8[: ow.shape[0]] = self._f32("conv_out.bias")
+        b8[: ow.shape[0]] = ob
         self.out_conv = Lin(w8.contiguous(), b8, 32)
         self.n_moments = ow.shape[0]
 
