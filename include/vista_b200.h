@@ -127,10 +127,11 @@ int b200v_attention_spatial_v4(const void* q, int64_t ld_q, const void* k, int64
 int b200v_attention_spatial_v5(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                                void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
-/* Sixth generation: the v5 kernel with two softmax threads per query row (8 softmax warps per tile, 16 per CTA): each
- * thread holds 64 scores, the halves of a row exchange their maximum through shared memory, vote on the lazy rescale
- * tile-wide and publish their P chunks in parallel — two warps per scheduler keep the MUFU fed during a tile's turn. */
-int b200v_attention_spatial_v6(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+/* Seventh generation (v6 — two softmax threads per row — measured slower and was dropped, profiles/r02_attn6_variant_matrix.txt):
+ * v5 with S, P and O in separate tensor-memory columns.  S(j+1) of a tile is issued as soon as its softmax threads have
+ * READ S(j) instead of behind PV(j), so the tensor pipe — the bound of this kernel at head dim 64, where every MMA sits on
+ * the ~96-cycle instruction floor — always has independent work queued; the row sum moves into the row's thread. */
+int b200v_attention_spatial_v7(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                                void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
 /* Temporal self-attention over the T frames of each pixel (seq len T <= 32, head dim 64).

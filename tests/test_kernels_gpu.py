@@ -13,7 +13,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 # spatial-attention kernel generations under test; 4 (P in tensor memory) is experimental and opt-in
-ATTN_IMPLS = [int(v) for v in os.environ.get("VISTA_B200_TEST_ATTN_IMPLS", "1,2,3,5").split(",")] \
+ATTN_IMPLS = [int(v) for v in os.environ.get("VISTA_B200_TEST_ATTN_IMPLS", "1,2,3,5,7").split(",")] \
     + ([4] if os.environ.get("VISTA_B200_TEST_ATTN4") == "1" else [])
 
 

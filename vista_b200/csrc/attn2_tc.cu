@@ -324,10 +324,9 @@ extern "C" int b200v_attention_spatial_v2(const void* q, int64_t ld_q, const voi
   p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   const int smem_bytes = 1024 + 1024 + 11 * kT2Bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  if (vb::first_use_on_device(attr_set)) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(attn2_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
   }
   dim3 grid((seq + 2 * kT2 - 1) / (2 * kT2), heads, frames);
   attn2_spatial_kernel<<<grid, 320, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);

@@ -262,10 +262,9 @@ extern "C" int b200v_attention_spatial(const void* q, int64_t ld_q, const void* 
   // 64-element groups along N) is unused for N = 64.
   p.v_lbo = kTileBytes; p.v_sbo = 1024; p.v_kstep = 2048;
   const int smem_bytes = 1024 + 1024 + 9 * kTileBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  if (vb::first_use_on_device(attr_set)) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
   }
   dim3 grid((seq + kTile - 1) / kTile, heads, frames);
   attn_spatial_kernel<<<grid, 192, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);

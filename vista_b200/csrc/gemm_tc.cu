@@ -637,9 +637,9 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   static const Kern kStats[3] = {tapgemm_kernel<0, false, 0, false, false, 2, true>,
                                  tapgemm_kernel<0, false, 1, false, false, 2, true>,
                                  tapgemm_kernel<0, true, 0, false, false, 2, true>};
-  static bool attr_set = false;
+  static bool attr_set[64] = {false};
   static int max_clusters = 0;
-  if (!attr_set) {
+  if (vb::first_use_on_device(attr_set)) {
     for (int i = 0; i < 3; ++i)
       VB_CHECK_CUDA(cudaFuncSetAttribute(kStats[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     for (int q = 0; q < 2; ++q)
@@ -657,7 +657,6 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
       cudaGetLastError();
       max_clusters = device_sm_count() / 2;
     }
-    attr_set = true;
   }
   if (d->stats) {
     const long long total = (long long)p.m_tiles * p.n_tiles;

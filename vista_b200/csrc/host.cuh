@@ -12,6 +12,15 @@ namespace vb {
 void set_error(const char* fmt, ...);
 const char* last_error();
 int device_sm_count();
+// true the first time it is called with `flags` on the current device: function attributes
+// (cudaFuncAttributeMaxDynamicSharedMemorySize ...) are per device, a process may drive several
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
 
 #define VB_CHECK_CUDA(expr)                                                                        \
   do {                                                                                             \

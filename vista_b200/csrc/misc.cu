@@ -893,12 +893,11 @@ static int gn_stats_impl(const void* x, int64_t ldx, int32_t frames, int32_t tok
   dim3 grid((tokens_per_frame + chunk - 1) / chunk, frames);
   size_t smem = (size_t)rows * 2 * C * sizeof(float);
   if (smem < (size_t)groups * 8 * 2 * sizeof(double)) smem = (size_t)groups * 8 * 2 * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  if (vb::first_use_on_device(attr_set)) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     VB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
   }
   VB_REQUIRE(smem <= 160 * 1024, "groupnorm_stats: shared memory %zu too large", smem);
 #define VB_GN_STATS(JT)                                                                                              \

@@ -74,10 +74,9 @@ extern "C" int b200v_debug_mma_probe(int32_t M, int32_t N, int32_t iters, int32_
   VB_REQUIRE(N >= 8 && N <= 256 && N % (M == 128 ? 16 : 8) == 0, "mma_probe: N=%d invalid for M=%d", N, M);
   VB_REQUIRE(iters > 0 && n_acc >= 1 && n_acc * N <= (a_in_tmem ? 480 : 512), "mma_probe: iters / n_acc out of range");
   const int smem_bytes = 1024 + 1024 + (128 + 256) * 128;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  if (vb::first_use_on_device(attr_set)) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
   }
   mma_probe_kernel<<<n_ctas, 128, smem_bytes, (cudaStream_t)stream>>>(M, N, iters, n_acc, a_mn_major, a_in_tmem,
                                                                        cycles_per_mma);

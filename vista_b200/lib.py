@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvista_b200.so")
-SOURCES = ["host.cu", "gemm_tc.cu", "attn_tc.cu", "attn2_tc.cu", "attn5_tc.cu", "attn6_tc.cu", "misc.cu", "glue.cu", "mma_probe.cu"]
+SOURCES = ["host.cu", "gemm_tc.cu", "attn_tc.cu", "attn2_tc.cu", "attn5_tc.cu", "attn7_tc.cu", "misc.cu", "glue.cu", "mma_probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -99,7 +99,7 @@ SIGNATURES = {
     "b200v_attention_spatial_v3": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v4": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v5": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
-    "b200v_attention_spatial_v6": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
+    "b200v_attention_spatial_v7": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_groupnorm_from_partials": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P],
     "b200v_groupnorm_chunk": [],

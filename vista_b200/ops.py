@@ -86,6 +86,10 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def _rows(t: torch.Tensor) -> Tuple[int, int]:
     assert t.dim() == 2 and t.stride(1) == 1, "token-major 2-D view with unit channel stride expected"
+    # launches go to the CURRENT device's current stream: a tensor living elsewhere would be dereferenced on the wrong GPU
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"vista_b200: tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}; "
+                           "wrap the call in torch.cuda.device(tensor.device)")
     return t.shape[0], t.stride(0)
 
 
@@ -192,16 +196,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
     return out
 
 
-# Spatial-attention kernel generation.  0 (default): by shape — v5 (persistent, two query tiles per CTA in ping-pong, P in
-# tensor memory) for long sequences, v3 (one tile per CTA, two CTAs per SM) for the short ones of the inner levels;
-# 1 / 2 / 3 / 4 / 5 force one generation.
+# Spatial-attention kernel generation.  0 (default): by shape — v7 (persistent, two query tiles per CTA, P in tensor
+# memory, S / P / O in separate columns so that S(j+1) runs ahead of the softmax) for long sequences, v3 (one tile per CTA,
+# two CTAs per SM) for the short ones of the inner levels; 1 / 2 / 3 / 4 / 5 / 7 force one generation.
 ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "0"))
 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
     l = _lib.load()
     fn = {1: l.b200v_attention_spatial, 2: l.b200v_attention_spatial_v2, 3: l.b200v_attention_spatial_v3,
-          4: l.b200v_attention_spatial_v4, 5: l.b200v_attention_spatial_v5, 6: l.b200v_attention_spatial_v6}[impl or ATTN_IMPL or (5 if seq >= 2048 else 3)]
+          4: l.b200v_attention_spatial_v4, 5: l.b200v_attention_spatial_v5, 7: l.b200v_attention_spatial_v7}[impl or ATTN_IMPL or (7 if seq >= 2048 else 3)]
     _count(1)
     _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
                 2.0 * 4 * frames * seq * heads * 64)

@@ -181,15 +181,38 @@ class ShardedUNetRuntime(UNetRuntime):
             self._frame_tables[key] = tab
         return tab
 
+    def _kv_direct(self, nb: int) -> bool:
+        """The K|V projection can be written straight into the all-gather's send layout when that layout has no padding
+        rows between the clips of this rank: one clip (the CFG-split layouts), or every rank owning T_pad frames."""
+        return nb == 1 or self.T == self.T_pad
+
+    def _svt_tqkv(self, n, L, M: int, Cc: int, nb: int, hw: int):
+        """q|k|v projection of the temporal attention.  Direct mode: two launches over the row blocks of the fused weight —
+        q into the q buffer, K|V straight into the send buffer of the all-gather (no staging copy of the largest tensor of
+        the exchange); otherwise the fused projection (the copy happens in _attn_temporal)."""
+        if not self._kv_direct(nb):
+            return super()._svt_tqkv(n, L, M, Cc, nb, hw)
+        lin = L["tqkv"]
+        sub = self._tap_w.get(("qkv", lin.w.data_ptr()))
+        if sub is None:
+            sub = (Lin(lin.w[:Cc], None, ops.pick_tile_n(Cc)), Lin(lin.w[Cc:], None, ops.pick_tile_n(2 * Cc)))
+            self._tap_w[("qkv", lin.w.data_ptr())] = sub
+        qkv = self.buf("tr.qkv", M, 3 * Cc)
+        send = self.buf("kv.send", nb * self.T_pad * hw, 2 * Cc)
+        self.gemm(n, sub[0], qkv[:, :Cc])
+        self.gemm(n, sub[1], send[:M])
+        return qkv
+
     def _attn_temporal(self, qkv, o, nb: int, hw: int, heads: int, Cc: int):
         T, Tp, W = self.T, self.T_pad, self.world
         send = self.buf("kv.send", nb * Tp * hw, 2 * Cc)
         recv = self.buf("kv.recv", W * nb * Tp * hw, 2 * Cc)
-        # the K|V column block of the fused q|k|v projection as a strided (clip, frame, pixel, 2C) view
-        kv = qkv.as_strided((nb, T, hw, 2 * Cc), (T * hw * qkv.stride(0), hw * qkv.stride(0), qkv.stride(0), 1),
-                            qkv.storage_offset() + Cc)
-        dst = send.view(nb, Tp, hw, 2 * Cc)[:, :T]
-        _lib.tape_host(lambda: dst.copy_(kv), "kv staging copy")
+        if not self._kv_direct(nb):
+            # the K|V column block of the fused q|k|v projection as a strided (clip, frame, pixel, 2C) view
+            kv = qkv.as_strided((nb, T, hw, 2 * Cc), (T * hw * qkv.stride(0), hw * qkv.stride(0), qkv.stride(0), 1),
+                                qkv.storage_offset() + Cc)
+            dst = send.view(nb, Tp, hw, 2 * Cc)[:, :T]
+            _lib.tape_host(lambda: dst.copy_(kv), "kv staging copy")
         _lib.tape_host(lambda: dist.all_gather_into_tensor(recv, send, group=self.group), f"kv all_gather C={Cc} hw={hw}")
         self.comm_bytes += recv.numel() * 2
         tab = self._frame_table(nb, hw)

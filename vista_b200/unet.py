@@ -231,6 +231,12 @@ class UNetRuntime:
         """context (B,1,3456) / y (B,768): everything that does not depend on sigma or the step."""
         T = self.T
         B = context.shape[0]
+        # both cross-attentions are folded to per-frame constants, which is exact for ONE key token only
+        # (encoders/modules.py:514-516, video_attention.py:256-257): refuse anything else instead of using token 0
+        from .spec import ACTION_DIM
+        want = self.cfg.context_dim + (ACTION_DIM if self.cfg.action_control else 0)
+        if context.dim() != 3 or context.shape[1] != 1 or context.shape[2] != want:
+            raise NotImplementedError(f"vista_b200: crossattn context must be (B, 1, {want}); got {tuple(context.shape)}")
         ctx16 = self.buf("cond.ctx", B, context.numel() // B)
         ctx16.copy_(context.reshape(B, -1))
         y16 = self.buf("cond.y", B, y.shape[-1])
@@ -282,6 +288,10 @@ class UNetRuntime:
         """(3,1,1) convolution over the frames of each clip (zero padded at the clip ends)."""
         return self.gemm(a, lin, out, taps=ops.TAPS_T3, geom=(hw, self.T, nb), **epi)
 
+    def _svt_tqkv(self, n, L, M: int, Cc: int, nb: int, hw: int):
+        """Fused q|k|v projection of the temporal attention (a hook: the frame-sharded runtime splits it)."""
+        return self.gemm(n, L["tqkv"], self.buf("tr.qkv", M, 3 * Cc))
+
     def _attn_temporal(self, qkv, o, nb: int, hw: int, heads: int, Cc: int):
         return ops.attention_temporal(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], o, nb, self.T, hw, heads)
 
@@ -307,7 +317,7 @@ class UNetRuntime:
         g = self.gemm(n, L["ffin1"], self.buf("tr.g", M, 4 * Cc))
         u1 = self.gemm(g, L["ffin2"], self.buf("tr.u1", M, Cc), res1=t2, rowvec=pos, rv_div=hw, rv_mod=T)
         n = self._ln(u1, self.buf("tr.n", M, Cc), L["tln1"])
-        qkv = self.gemm(n, L["tqkv"], self.buf("tr.qkv", M, 3 * Cc))
+        qkv = self._svt_tqkv(n, L, M, Cc, nb, hw)
         self._attn_temporal(qkv, o, nb, hw, t.heads, Cc)
         u2 = self.gemm(o, L["tout"], self.buf("tr.t1", M, Cc), res1=u1, rowvec=self.cond["tm"][p], rv_div=T * hw, rv_mod=nb)
         n = self._ln(u2, self.buf("tr.n", M, Cc), L["tln3"])
