@@ -180,7 +180,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a dead rank must fail the job in minutes, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("VISTA_B200_NCCL_TIMEOUT", "180"))))
     from vista_b200 import lib, ops
     from vista_b200.diffusion import B200Denoiser
     from vista_b200.modules import B200Wrapper

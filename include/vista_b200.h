@@ -83,6 +83,11 @@ typedef struct b200v_gemm_desc {
   float* stats;
   int64_t stats_ld;
   int32_t stats_col0;
+  /* a_mode 1 only: the A view has h_pad extra rows of H before and after the H rows that produce output (extents
+   * c, W, H + 2 h_pad, NB; `a` points at the first extra row).  Tap offsets are taken relative to the first OUTPUT row, so
+   * a (3,1,1) convolution over frames reads its neighbours' boundary frames from the halo slots instead of zero padding:
+   * the frame-sharded temporal convolution in ONE launch (openaimodel.py:190-193 across shards). */
+  int32_t h_pad;
 } b200v_gemm_desc;
 
 int b200v_gemm(const b200v_gemm_desc* d, void* stream);
@@ -101,36 +106,18 @@ int b200v_groupnorm_from_partials(const float* partials, int64_t stats_ld, int32
  * split / merge copies at :370-378, :409-414).  q/k/v are column slices of token-major buffers:
  * element (frame f, token t, head h, dim d) of q is q[(f*seq + t)*ld_q + h*64 + d].
  * ---------------------------------------------------------------------------------------------- */
-int b200v_attention_spatial(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
-                            void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
-
-/* Same contract, second-generation kernel: two 128-query tiles per CTA in ping-pong (two softmax
- * warpgroups), output accumulator and row sum kept in TMEM (ones-column trick), lazy rescaling. */
-int b200v_attention_spatial_v2(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
-                               void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
-
-/* Third generation: one 128-query tile per CTA, two CTAs per SM, two threads per query row (eight softmax
- * warps), S consumed in 32-column chunks, part of the exponentials on the FMA pipe. */
+/* Short sequences (the inner UNet levels): one 128-query tile per CTA, two CTAs per SM, two softmax threads per query row
+ * (eight softmax warps), P through swizzled shared memory, O and the row sum in tensor memory with lazy rescaling. */
 int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                                void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
-/* EXPERIMENTAL (opt-in, VISTA_B200_ATTN=4; not validated on hardware at the time of writing): the v3 kernel with P kept in
- * tensor memory (tcgen05.st into the consumed S columns, O += P V issued with the A operand in TMEM) instead of a
- * shared-memory round trip. */
-int b200v_attention_spatial_v4(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
-                               void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
-
-/* Fifth generation (the default for long sequences): persistent kernel, one CTA per SM walking (frame, head, 256-query
- * block) work items; two 128-query tiles per CTA in ping-pong, one thread per query row, P written back into tensor
- * memory over the consumed scores (tcgen05.st) and O += P [V | 1] issued with the A operand in TMEM; K / V in 3-deep
- * TMA rings shared by the two tiles, Q of the next item prefetched into a second buffer. */
-int b200v_attention_spatial_v5(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
-                               void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
-
-/* Seventh generation (v6 — two softmax threads per row — measured slower and was dropped, profiles/r02_attn6_variant_matrix.txt):
- * v5 with S, P and O in separate tensor-memory columns.  S(j+1) of a tile is issued as soon as its softmax threads have
- * READ S(j) instead of behind PV(j), so the tensor pipe — the bound of this kernel at head dim 64, where every MMA sits on
- * the ~96-cycle instruction floor — always has independent work queued; the row sum moves into the row's thread. */
+/* Long sequences (the default from 2048 tokens): persistent kernel, one CTA per SM walking (frame, head, 256-query block)
+ * work items; two 128-query tiles per CTA, one thread per query row, K / V in 3-deep TMA rings shared by the tiles, Q of
+ * the next item prefetched.  S, P and O live in separate tensor-memory columns (2 x (128 + 64 + 64) = 512): P is written
+ * with tcgen05.st and O += P V is issued with the A operand in TMEM; S(j+1) of a tile is issued as soon as its softmax
+ * threads have READ S(j), so the tensor pipe — the bound of this kernel at head dim 64, where every MMA sits on the
+ * ~96-cycle instruction floor — always has independent work queued; the row sum is kept by the row's thread.
+ * (Generations 1, 2, 4, 5, 6 were measured and removed: profiles/r02_ncu_attn5.md.) */
 int b200v_attention_spatial_v7(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                                void* out, int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream);
 
@@ -235,13 +222,6 @@ int b200v_sampler_update(float* x, const float* net_out /* [2T*h*w, ld_net] fp32
                          int64_t ld_net, const float* cond_frame, const float* mask, const float* scales /* [T] */, const float* sigmas, int32_t* step_idx,
                          int32_t num_steps, int32_t T, int32_t h, int32_t w, void* stream);
 
-/* Diagnostic (not on the product path): SM cycles one tcgen05.mma kind::f16 K=16 (shared-memory operands, M in
- * {64,128}, N) occupies the tensor pipe, from a train of 4*iters MMAs cycling over n_acc accumulators; one value per
- * CTA in cycles_per_mma[n_ctas].  Drives the tile policy (profiles/r01_umma_n_sweep.md); tools/mma_probe.py. */
-int b200v_debug_mma_probe(int32_t M, int32_t N, int32_t iters, int32_t n_acc, int32_t a_mn_major,
-                          int32_t a_in_tmem /* A operand from tensor memory instead of shared memory */,
-                          float* cycles_per_mma, int32_t n_ctas, void* stream);
-
 /* VAE decoder helpers.
  *   softmax_rows : fp32 scores -> fp16 probabilities, one row per block (mid.attn_1 single-head d=512
  *                  attention, vwm/modules/diffusionmodules/model.py:158-170, done as GEMM-softmax-GEMM)
@@ -278,6 +258,31 @@ int b200v_rollout_advance(float* sample, const float* z0, float* samples_z, floa
 int b200v_ensemble_reward_scratch(void);
 int b200v_ensemble_reward(const float* const* members_dev, int32_t K, int64_t n, double* partial, uint32_t* ticket,
                           float* out2, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Collectives of the frame-sharded step over NVLink peer memory (csrc/peer.cu).  A "window" is device memory
+ * of one rank that its peers map (CUDA IPC) and store into; flags inside the window order the traffic (system-scope
+ * release / acquire), sequence numbers are device-resident counters bumped by the kernels, so the calls below are plain
+ * stream-ordered launches that a CUDA graph can replay.
+ *   peer_alloc / open / close / free : window lifetime; handle64 = 64-byte cudaIpcMemHandle_t to hand to the peers.
+ *   peer_allreduce_f64 : data[n] (n <= b200v_peer_allreduce_max()) summed over `world` ranks in RANK ORDER (same bits on
+ *       every rank).  windows_dev = device array [world] of window base pointers as mapped by THIS rank (own window at
+ *       [rank]); slot_off / flag_off = byte offsets, identical on all ranks, of 2 * world * max doubles and 2 * 16 uint32.
+ *   peer_put : `rows` rows of row_bytes (multiple of 16) from src (pitch src_pitch) to each of n_dst (<= 8) destinations
+ *       (pitch dst_pitch), then flag[d] = next sequence number of `counter` (release, after a system fence; last block by
+ *       `ticket`, a zeroed uint32 that resets itself).
+ *   peer_wait : spin (one thread per flag, bounded) until the n LOCAL flags reach the next sequence number of `counter`.
+ * ---------------------------------------------------------------------------------------------- */
+int b200v_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int b200v_peer_open(const void* handle64, void** ptr);
+int b200v_peer_close(void* ptr);
+int b200v_peer_free(void* ptr);
+int b200v_peer_allreduce_max(void);
+int b200v_peer_allreduce_f64(double* data, int32_t n, void* const* windows_dev, int64_t slot_off, int64_t flag_off, int32_t rank,
+                             int32_t world, uint32_t* counter, void* stream);
+int b200v_peer_put(const void* src, int64_t src_pitch, int64_t rows, int64_t row_bytes, void* const* dsts_dev, int64_t dst_pitch,
+                   uint32_t* const* flags_dev, int32_t n_dst, uint32_t* counter, uint32_t* ticket, void* stream);
+int b200v_peer_wait(const uint32_t* const* flags_dev, int32_t n, uint32_t* counter, void* stream);
 
 /* Layout converters at the boundary: NCHW fp32 <-> token-major (NHWC) fp16/fp32. */
 int b200v_nchw_to_tokens(const float* x, void* out_f16, int64_t ldo, int32_t NB, int32_t C, int32_t H, int32_t W,

@@ -12,9 +12,8 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-# spatial-attention kernel generations under test; 4 (P in tensor memory) is experimental and opt-in
-ATTN_IMPLS = [int(v) for v in os.environ.get("VISTA_B200_TEST_ATTN_IMPLS", "1,2,3,5,7").split(",")] \
-    + ([4] if os.environ.get("VISTA_B200_TEST_ATTN4") == "1" else [])
+# spatial-attention kernels under test: 3 (short sequences) and 7 (long sequences), each on every shape
+ATTN_IMPLS = [int(v) for v in os.environ.get("VISTA_B200_TEST_ATTN_IMPLS", "3,7").split(",")]
 
 
 @pytest.fixture(scope="module")
@@ -190,6 +189,35 @@ def test_gemm_temporal_conv(ops, nb, T, S, Cc):
     x5 = x.float().permute(0, 3, 1, 2)[..., None]         # b c t s 1
     ref = F.conv3d(x5, wt.float(), bias, padding=(1, 0, 0))[..., 0].permute(0, 2, 3, 1).reshape(-1, Cc)
     check(out, 0.4 * ref + res.float(), name="tconv")
+
+
+@pytest.mark.parametrize("nb,T,S,Cc", [(1, 7, 128, 64), (1, 6, 144, 128), (2, 5, 256, 64)])
+def test_gemm_temporal_conv_with_halo_frames(ops, nb, T, S, Cc):
+    """h_pad = 1: the (3,1,1) convolution of a frame shard reads its neighbours' boundary frames from the halo slots of the
+    extended tensor [prev | T local | next] in ONE launch — equal to the same frames cut out of the convolution of the
+    longer clip (and to zero padding where a halo slot holds zeros: the clip ends)."""
+    full = rnd(nb, T + 2, S, Cc, seed=33)                 # the T local frames with one real neighbour frame on each side
+    wt = rnd(Cc, Cc, 3, 1, 1, seed=34, scale=(3 * Cc) ** -0.5)
+    bias = rnd(Cc, seed=35, dtype=torch.float32)
+    w2 = wt[:, :, :, 0, 0].permute(0, 2, 1).reshape(Cc, 3 * Cc).contiguous()
+    out = torch.empty(nb * T * S, Cc, dtype=torch.float16, device=dev())
+    stats = torch.zeros(-(-nb * T * S // 128) * 4, Cc, 2, dtype=torch.float32, device=dev()) if S % 128 == 0 else None
+    ops.gemm(full.reshape(-1, Cc), w2, out, taps=ops.TAPS_T3, geom=(S, T, nb), bias=bias, h_pad=1, stats=stats)
+    torch.cuda.synchronize()
+    x5 = full.float().permute(0, 3, 1, 2)[..., None]      # b c (T+2) s 1
+    ref = F.conv3d(x5, wt.float(), bias, padding=(1, 0, 0))[..., 0][:, :, 1:T + 1].permute(0, 2, 3, 1).reshape(-1, Cc)
+    check(out, ref, name="tconv+halo")
+    if stats is not None:                                  # fused statistics see the halo contributions
+        got = stats[..., 0].sum(0)
+        assert torch.allclose(got, out.float().sum(0), rtol=2e-3, atol=2e-2)
+    # zero halos == zero padding of the plain launch
+    full[:, 0] = 0
+    full[:, T + 1] = 0
+    out2 = torch.empty_like(out)
+    ops.gemm(full.reshape(-1, Cc), w2, out, taps=ops.TAPS_T3, geom=(S, T, nb), bias=bias, h_pad=1)
+    ops.gemm(full[:, 1:T + 1].reshape(-1, Cc), w2, out2, taps=ops.TAPS_T3, geom=(S, T, nb), bias=bias)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
 
 
 # ------------------------------------------------------------------------------------------ attention

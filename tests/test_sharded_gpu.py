@@ -20,8 +20,11 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import datetime
+    # a rank that dies (a trapped peer wait, an assertion) must not leave the others in a 10-minute NCCL watchdog wait
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
     try:
+        _peer_primitives(rank, world, dev)
         from test_sampler_gpu import make_sampler
         from vista_b200.diffusion import B200Denoiser, Denoiser
         from vista_b200.modules import B200Wrapper, VideoUNet
@@ -74,15 +77,77 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _peer_primitives(rank, world, dev):
+    """csrc/peer.cu over a PeerWindow of all ranks: the rank-ordered fp64 all-reduce (bit-identical on every rank, equal
+    to the sum of the contributions), put + flag + wait in a ring (double use of the same slots), 20 rounds each."""
+    import torch.distributed as dist
+    from vista_b200 import ops
+    from vista_b200.peer import PeerWindow
+    win = PeerWindow(None, 8 << 20, dev)
+    amax = ops._lib.load().b200v_peer_allreduce_max()
+    slot, flag = win.region("ar.slots", 2 * 16 * amax * 8), win.region("ar.flags", 2 * 16 * 4)
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    n = 100
+    for it in range(20):
+        g = torch.Generator().manual_seed(1000 * it + rank)
+        mine = torch.randn(n, generator=g, dtype=torch.float64).to(dev)
+        data = mine.clone()
+        ops.peer_allreduce_f64(data, win.windows_dev, slot, flag, rank, world, counter)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        want = parts[0].clone()
+        for p in parts[1:]:
+            want += p                      # rank order, like the kernel
+        assert torch.equal(data, want), f"peer all-reduce round {it}: max diff {float((data - want).abs().max())}"
+    # ring: rank r stores a pattern into rank r+1's inbox, waits for the one from rank r-1
+    rows, rb = 64, 4096
+    inbox = win.region("ring.inbox", rows * rb)
+    fl = win.region("ring.flag", 256)
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    dst = win.ptr_array([win.remote(nxt, inbox)])
+    dflag = win.ptr_array([win.remote(nxt, fl)])
+    myflag = win.ptr_array([win.local(fl)])
+    c_put, tk, c_wait = (torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(3))
+    box = win.tensor(inbox, (rows, rb // 4), torch.int32)
+    for it in range(20):
+        src = torch.full((rows, rb // 4), 1000 * it + rank, dtype=torch.int32, device=dev)
+        ops.peer_put(src.data_ptr(), rb, rows, rb, dst, rb, dflag, 1, c_put, tk, "ring")
+        ops.peer_wait(myflag, 1, c_wait, "ring")
+        got = box.clone()
+        torch.cuda.synchronize()
+        assert bool((got == 1000 * it + prv).all()), f"ring round {it}: got {int(got[0, 0])}, want {1000 * it + prv}"
+        dist.barrier()                     # the inbox is single-buffered: nobody runs two rounds ahead
+    torch.cuda.synchronize()
+    dist.barrier()
+    win.close()
+
+
 def _run_world(world: int):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() + 17 * world) % 1000
+    import queue as _queue
+    import time
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    outs = [q.get(timeout=900) for _ in procs]
+    # fail fast: a rank that dies (import error, assertion, trapped kernel) would otherwise leave the others waiting in a
+    # collective until a watchdog fires, holding every GPU of the box
+    outs, deadline = [], time.time() + 420
+    try:
+        while len(outs) < world:
+            try:
+                outs.append(q.get(timeout=2))
+            except _queue.Empty:
+                dead = [p for p in procs if p.exitcode not in (None, 0)]
+                assert not dead, f"rank process(es) exited with {[p.exitcode for p in dead]}"
+                assert time.time() < deadline, "sharded workers timed out"
+    finally:
+        if len(outs) < world:
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

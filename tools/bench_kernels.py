@@ -31,7 +31,7 @@ def timeit(name, fn, *a, **k):
     _timeit(name, fn, *a, **k)
 
 
-for (M, C, geom) in ((460800, 320, (128, 72, 50)), (115200, 640, (64, 36, 50))):
+for (M, C, geom) in ((460800, 320, (128, 72, 50)), (115200, 640, (64, 36, 50)), (28800, 1280, (32, 18, 50))):
     x = (torch.randn(M, C, device=dev) * 0.5).half()
     w = torch.randn(8 * C, C, device=dev) * C ** -0.5
     b = torch.randn(8 * C, device=dev) * 0.05
@@ -54,7 +54,7 @@ for (M, C, geom) in ((460800, 320, (128, 72, 50)), (115200, 640, (64, 36, 50))):
     heads, seq = C // 64, geom[0] * geom[1]
     o = torch.empty(M, C, dtype=torch.float16, device=dev)
     qkv = torch.randn(M, 3 * C, device=dev).half()
-    impls = tuple(int(v) for v in os.environ["BENCH_ATTN_IMPLS"].split(",")) if os.environ.get("BENCH_ATTN_IMPLS") else ((3,) if only else (1, 2, 3))
+    impls = tuple(int(v) for v in os.environ["BENCH_ATTN_IMPLS"].split(",")) if os.environ.get("BENCH_ATTN_IMPLS") else (3, 7)
     for impl in impls:
         timeit(f"attention spatial v{impl} seq={seq} heads={heads}",
                lambda: ops.attention_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, 50, seq, heads, impl=impl),

@@ -5,9 +5,9 @@
 // issue + completion of the whole train is reported per CTA.  Operand contents are irrelevant (zeros).
 // This measurement decides tile shapes (profiles/r01_umma_n_sweep.md); it is not on the
 // product path.
-#include "../../include/vista_b200.h"
-#include "host.cuh"
-#include "ptx.cuh"
+#include <stdint.h>
+#include "../../vista_b200/csrc/host.cuh"
+#include "../../vista_b200/csrc/ptx.cuh"
 
 namespace vb {
 

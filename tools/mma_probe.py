@@ -3,9 +3,19 @@ Usage: python tools/mma_probe.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import ctypes, subprocess
 import torch
 from vista_b200 import lib
-l = lib.load()
+# the probe is a diagnostic, not product code: it is built here into its own library (linked against the product's host
+# helpers through libvista_b200.so) instead of shipping inside it
+lib.load()
+so = os.path.join(ROOT, "tools", "libvista_b200_probe.so")
+src = os.path.join(ROOT, "tools", "csrc", "mma_probe.cu")
+if not os.path.isfile(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    subprocess.run(["nvcc", *lib.NVCC_FLAGS, "-shared", "-o", so, src, lib.LIB_PATH, "-Xlinker", "-rpath," + lib.PKG_DIR], check=True)
+l = ctypes.CDLL(so)
+l.b200v_debug_mma_probe.restype = ctypes.c_int
+l.b200v_debug_mma_probe.argtypes = [ctypes.c_int32] * 6 + [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
 dev = torch.device("cuda:0")
 n_ctas = torch.cuda.get_device_properties(dev).multi_processor_count
 out = torch.zeros(n_ctas, dtype=torch.float32, device=dev)

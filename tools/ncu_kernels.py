@@ -42,7 +42,7 @@ if "conv1280" in which:
 if "attn" in which:
     qkv = torch.randn(M, 3 * C, device=dev).half()
     o = torch.empty(M, C, dtype=torch.float16, device=dev)
-    for impl in (5,):
+    for impl in (7,):
         for _ in range(2):
             ops.attention_spatial(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, 50, 9216, 5, impl=impl)
 if "tattn" in which:

@@ -1,14 +1,7 @@
-// Spatial self-attention v2 (head dim 64, non-causal): two 128-query tiles per CTA in ping-pong.
-//   warps 0-3 : softmax warpgroup of tile A     warps 4-7 : softmax warpgroup of tile B
-//   warp 8    : TMA producer (Q_A, Q_B once; K/V blocks of 128 keys, 2-deep ring)
-//   warp 9    : TMEM owner + single-thread tcgen05.mma issuer
-// Per KV block and tile:  S = Q K^T (M128 N128 K64) -> softmax warpgroup -> P (fp16, swizzled smem)
-//                         O += P [V | 1] (M128 N80 K128): the accumulator stays in TMEM across blocks and
-// column 64 accumulates the row sum of exactly the fp16 P values that multiplied V (B operand = the V TMA
-// tile as MN-major atom 0 plus a constant "ones" atom), so the softmax threads neither add nor keep O.
-// The running maximum is applied lazily: O (and with it the row sum) is rescaled in TMEM only when the
-// block maximum exceeds the maximum in use by more than 2^8; P stays below 2^8 otherwise (fp16 is fine).
-// While warpgroup A runs the softmax of block j, the tensor core works on tile B, and vice versa.
+// Spatial self-attention for SHORT sequences (head dim 64, non-causal): the third-generation kernel (one 128-query tile per
+// CTA, two CTAs per SM, two softmax threads per row, P through swizzled shared memory, O and the row sum in tensor memory
+// with lazy rescaling).  Long sequences run the persistent kernel of attn7_tc.cu.  Generations 1, 2, 4, 5, 6 are gone from
+// the library; their measurements are in profiles/ (r01_step_breakdown_v*.md, r02_attn*_variant_matrix.txt).
 #include <stdlib.h>
 
 #include "../../include/vista_b200.h"
@@ -74,265 +67,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return p;
 }
 
-// 10 warps are allocated as 12 (granularity 4): at most 168 registers per thread
-__global__ void __launch_bounds__(320, 1)
-attn2_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* kv_full = q_full + 1;    // [2]
-  uint64_t* kv_empty = kv_full + 2;  // [2]
-  uint64_t* s_full = kv_empty + 2;   // [2] per tile
-  uint64_t* p_full = s_full + 2;     // [2] per tile
-  uint64_t* o_full = p_full + 2;     // [2] per tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-  uint8_t* sQ = smem + 1024;                // 2 tiles
-  uint8_t* sK = sQ + 2 * kT2Bytes;          // 2 stages
-  uint8_t* sV = sK + 2 * kT2Bytes;          // 2 stages
-  uint8_t* sOnes = sV + 2 * kT2Bytes;       // constant B atom: column 0 = 1, rest 0
-  uint8_t* sP = sOnes + kT2Bytes;           // 2 tiles x 2 sub-tiles of 64 keys
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * kT2;
-  const int head = blockIdx.y;
-  const int frame = blockIdx.z;
-  const int n_kv = p.n_kv;
-
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&o_full[i], 1);
-    }
-    fence_barrier_init();
-  }
-  // ones atom: row k (128 B) holds fp16 1.0 in logical column 0 -> 16-byte chunk 0 lives at slot (0 ^ (k & 7))
-  for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {
-    const int row = i >> 3, slot = i & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (slot == (row & 7)) v.x = 0x00003C00u;
-    *reinterpret_cast<uint4*>(sOnes + row * 128 + slot * 16) = v;
-  }
-  fence_proxy_async_smem();
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464)
-
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * kT2Bytes);
-      tma_load_3d(sQ, &tmQ, q_full, head * 64, q0, frame);
-      tma_load_3d(sQ + kT2Bytes, &tmQ, q_full, head * 64, q0 + kT2, frame);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1, 21);
-        mbar_expect_tx(&kv_full[st], 2 * kT2Bytes);
-        tma_load_3d(sK + st * kT2Bytes, &tmK, &kv_full[st], head * 64, j * kT2, frame);
-        tma_load_3d(sV + st * kT2Bytes, &tmV, &kv_full[st], head * 64, j * kT2, frame);
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0, 0);
-      const uint32_t idesc_o = make_idesc_f16(128, 80, 0, 0, 1);   // B = [V | ones] MN-major, N = 64 + 16
-      const uint32_t ones_base = smem_u32(sOnes);
-      auto issue_s = [&](int t, int j) {
-        const int st = j & 1;
-        const uint32_t q_base = smem_u32(sQ + t * kT2Bytes), k_base = smem_u32(sK + st * kT2Bytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base + t * 128, make_desc_sw128(q_base + k * 32, 16, 1024),
-                   make_desc_sw128(k_base + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](int t, int j) {
-        const int st = j & 1;
-        const uint32_t v_base = smem_u32(sV + st * kT2Bytes);
-        const uint32_t p_base = smem_u32(sP + t * 2 * kT2Bytes);
-        const uint32_t lbo = ones_base - v_base;   // second N atom (columns 64..79) = the ones atom
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t ad = make_desc_sw128(p_base + (k >> 2) * kT2Bytes + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_desc_sw128(v_base + k * 2048, lbo, 1024);
-          umma_f16(tmem_base + 256 + t * 128, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&o_full[t]);
-      };
-      mbar_wait(q_full, 0, 22);
-      mbar_wait(&kv_full[0], 0, 23);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const bool more = j + 1 < n_kv;
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], j & 1, 24);
-          tc_fence_after();
-          issue_pv(t, j);
-          if (t == 1) umma_commit(&kv_empty[j & 1]);   // both tiles are done with K_j / V_j
-          if (more) {
-            if (t == 0) {
-              mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1, 25);
-              tc_fence_after();
-            }
-            issue_s(t, j + 1);
-          }
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ softmax warpgroups
-    const int t = warp >> 2;                       // tile 0 / 1
-    const int r = (warp & 3) * 32 + lane;          // row in the tile == TMEM lane
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + t * 128 + lane_off;
-    const uint32_t tO = tmem_base + 256 + t * 128 + lane_off;
-    const uint32_t p_row = smem_u32(sP + t * 2 * kT2Bytes) + r * 128;
-    const int sw = r & 7;
-    float m_used = -INFINITY;
-
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[t], j & 1, 26);   // also implies PV_t(j-1) has completed (in-order commits)
-      tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(s + c * 32));
-      tmem_ld_wait();
-      const int kv_left = p.seq - j * kT2;
-      if (kv_left < kT2) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= kv_left) s[i] = 0xFF800000u;  // -inf
-      }
-      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent chains
-#pragma unroll
-      for (int i = 0; i < 128; i += 8) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          mxa[u] = max3(mxa[u], __uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1]));
-      }
-      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-      const float m_blk = mx * p.scale_log2;
-      // lazy rescale: only when the block maximum exceeds the maximum in use by more than 8 (factor 256)
-      const bool need = m_blk > m_used + 8.0f;
-      if (__any_sync(0xffffffffu, need)) {
-        const float m_new = need ? m_blk : m_used;
-        if (j > 0) {
-          const float alpha = need ? ex2_f(m_used - m_new) : 1.0f;
-#pragma unroll
-          for (int c = 0; c < 5; ++c) {   // 80 accumulator columns: 64 dims + row sum (+15 unused)
-            uint32_t ov[16];
-            tmem_ld16(tO + c * 16, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st16(tO + c * 16, ov);
-          }
-          tmem_st_wait();
-        }
-        m_used = m_new;
-      }
-      // P = exp2(s*scale - m_used) -> fp16 -> swizzled K-major smem (A operand of the PV MMA)
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float x0 = fmaf(__uint_as_float(s[c * 8 + 2 * i]), p.scale_log2, -m_used);
-          const float x1 = fmaf(__uint_as_float(s[c * 8 + 2 * i + 1]), p.scale_log2, -m_used);
-          const float p0 = (i < VB_ATTN_POLY_OF_4) ? exp2_poly(x0) : ex2_f(x0);
-          const float p1 = (i < VB_ATTN_POLY_OF_4) ? exp2_poly(x1) : ex2_f(x1);
-          w[i] = pack_h2(p0, p1);
-        }
-        const uint32_t addr = p_row + (c >> 3) * kT2Bytes + (((c & 7) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                     : "memory");
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
-    }
-    // epilogue: O / rowsum
-    mbar_wait(&o_full[t], (n_kv - 1) & 1, 27);
-    tc_fence_after();
-    uint32_t ov[64], lv[16];
-    tmem_ld32(tO, *reinterpret_cast<uint32_t(*)[32]>(ov));
-    tmem_ld32(tO + 32, *reinterpret_cast<uint32_t(*)[32]>(ov + 32));
-    tmem_ld16(tO + 64, lv);
-    tmem_ld_wait();
-    const float inv = 1.0f / __uint_as_float(lv[0]);
-    const int q = q0 + t * kT2 + r;
-    if (q < p.seq) {
-      uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + ((long long)frame * p.seq + q) * p.ld_o + head * 64;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          w[i] = pack_h2(__uint_as_float(ov[c * 8 + 2 * i]) * inv, __uint_as_float(ov[c * 8 + 2 * i + 1]) * inv);
-        *reinterpret_cast<uint4*>(op + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
 }  // namespace vb
-
-extern "C" int b200v_attention_spatial_v2(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
-                                          int64_t ld_v, void* out, int64_t ld_o, int32_t frames, int32_t seq,
-                                          int32_t heads, void* stream_) {
-  using namespace vb;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  VB_REQUIRE(q && k && v && out, "b200v_attention_spatial_v2: null pointer");
-  VB_REQUIRE(frames > 0 && seq > 0 && heads > 0, "b200v_attention_spatial_v2: bad sizes");
-  VB_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 8 == 0,
-             "b200v_attention_spatial_v2: row strides must be multiples of 8 elements");
-  CUtensorMap tm[3];
-  const void* ptrs[3] = {q, k, v};
-  const int64_t lds[3] = {ld_q, ld_k, ld_v};
-  for (int i = 0; i < 3; ++i) {
-    VB_REQUIRE((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, "b200v_attention_spatial_v2: unaligned pointer");
-    uint64_t dims[3] = {(uint64_t)heads * 64, (uint64_t)seq, (uint64_t)frames};
-    uint64_t strides[2] = {(uint64_t)lds[i] * 2, (uint64_t)lds[i] * 2 * seq};
-    uint32_t box[3] = {64, 128, 1};
-    uint32_t es[3] = {1, 1, 1};
-    if (encode_tmap_16bit(&tm[i], ptrs[i], 3, dims, strides, box, es, 0)) return 3;
-  }
-  Attn2Params p;
-  p.seq = seq;
-  p.n_kv = (seq + kT2 - 1) / kT2;
-  p.ld_o = ld_o;
-  p.out = out;
-  p.scale_log2 = 0.125f * 1.4426950408889634f;
-  const int smem_bytes = 1024 + 1024 + 11 * kT2Bytes;
-  static bool attr_set[64] = {false};
-  if (vb::first_use_on_device(attr_set)) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn2_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  }
-  dim3 grid((seq + 2 * kT2 - 1) / (2 * kT2), heads, frames);
-  attn2_spatial_kernel<<<grid, 320, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
-  VB_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
 
 // =================================================================================================
 // v3: one 128-query tile per CTA, TWO CTAs per SM (98 KB smem, 256 TMEM columns each), eight softmax
@@ -349,7 +84,7 @@ namespace vb {
 #define VB_ATTN3_POLY_OF_8 0   // of every 8 exponentials, this many use exp2_poly (FMA pipe) instead of MUFU
 #endif
 
-// TS = true (b200v_attention_spatial_v4, opt-in): P does not go through shared memory.  The softmax threads write it as
+// TS = true (the dropped v4; not instantiated): P does not go through shared memory.  The softmax threads write it as
 // packed fp16 into the TMEM columns of their own (already consumed) half of S with tcgen05.st, and O += P V is issued
 // with the A operand in TMEM.  The single-thread issue order keeps S(j+1) behind the PV(j) that reads the aliased
 // columns.  Motivation: with shared-memory operands every MMA costs ~90 ns however small N is (profiles/
@@ -594,7 +329,7 @@ attn3_spatial_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }  // namespace vb
 
 static int attn3_launch(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, void* out,
-                        int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream_, bool ts) {
+                        int64_t ld_o, int32_t frames, int32_t seq, int32_t heads, void* stream_) {
   using namespace vb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VB_REQUIRE(q && k && v && out, "b200v_attention_spatial_v3: null pointer");
@@ -629,14 +364,7 @@ static int attn3_launch(const void* q, int64_t ld_q, const void* k, int64_t ld_k
     VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
   dim3 grid((seq + kT2 - 1) / kT2, heads, frames);
-  if (ts) {
-    static bool ts_attr = false;
-    if (!ts_attr) {
-      VB_CHECK_CUDA(cudaFuncSetAttribute(attn3_spatial_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      ts_attr = true;
-    }
-    attn3_spatial_kernel<0, true><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
-  } else if (poly <= 0) attn3_spatial_kernel<0, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
+  if (poly <= 0) attn3_spatial_kernel<0, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
   else if (poly <= 2) attn3_spatial_kernel<2, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
   else if (poly == 3) attn3_spatial_kernel<3, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
   else attn3_spatial_kernel<4, false><<<grid, 384, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
@@ -647,11 +375,5 @@ static int attn3_launch(const void* q, int64_t ld_q, const void* k, int64_t ld_k
 extern "C" int b200v_attention_spatial_v3(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
                                           int64_t ld_v, void* out, int64_t ld_o, int32_t frames, int32_t seq,
                                           int32_t heads, void* stream) {
-  return attn3_launch(q, ld_q, k, ld_k, v, ld_v, out, ld_o, frames, seq, heads, stream, false);
-}
-
-extern "C" int b200v_attention_spatial_v4(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
-                                          int64_t ld_v, void* out, int64_t ld_o, int32_t frames, int32_t seq,
-                                          int32_t heads, void* stream) {
-  return attn3_launch(q, ld_q, k, ld_k, v, ld_v, out, ld_o, frames, seq, heads, stream, true);
+  return attn3_launch(q, ld_q, k, ld_k, v, ld_v, out, ld_o, frames, seq, heads, stream);
 }

@@ -522,7 +522,7 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   const long long K = (long long)d->ntaps * d->cin;
   CUtensorMap tmA, tmB;
   if (d->a_mode == 0) {
-    VB_REQUIRE(d->ntaps == 1, "b200v_gemm: linear mode takes one tap");
+    VB_REQUIRE(d->ntaps == 1 && d->h_pad == 0, "b200v_gemm: linear mode takes one tap and no halo rows");
     VB_REQUIRE(d->tokens > 0 && d->tokens < (1ll << 31) - 256, "b200v_gemm: tokens out of range");
     p.W = (int)d->tokens; p.H = 1; p.NB = 1;
     p.BW = 128; p.BH = 1; p.BB = 1;
@@ -545,8 +545,10 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
     p.tiles_h = (d->H + p.BH - 1) / p.BH;
     const int tiles_b = (d->NB + p.BB - 1) / p.BB;
     p.m_tiles = p.tiles_w * p.tiles_h * tiles_b;
-    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->NB};
-    uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * d->W, (uint64_t)d->lda * 2 * d->W * d->H};
+    VB_REQUIRE(d->h_pad >= 0 && d->h_pad <= 4, "b200v_gemm: h_pad=%d out of range", d->h_pad);
+    const uint64_t He = (uint64_t)d->H + 2ull * d->h_pad;     // rows of H in memory (halo rows before and after)
+    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->W, He, (uint64_t)d->NB};
+    uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * d->W, (uint64_t)d->lda * 2 * d->W * He};
     uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BB};
     uint32_t es[4] = {1, 1, 1, 1};
     if (encode_tmap_16bit(&tmA, d->a, 4, dims, strides, box, es, d->bf16)) return 3;
@@ -567,7 +569,7 @@ extern "C" int b200v_gemm(const b200v_gemm_desc* d, void* stream_) {
   p.ntaps = d->ntaps;
   p.kc_per_tap = d->cin / 64;
   for (int i = 0; i < 9; ++i) {
-    p.dh[i] = d->dh[i];
+    p.dh[i] = d->dh[i] + (d->a_mode == 1 ? d->h_pad : 0);   // TMA coordinates count from the first halo row
     p.dw[i] = d->dw[i];
   }
   p.N = d->N;

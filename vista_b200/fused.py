@@ -49,11 +49,38 @@ class _LoopState:
         self.split = None            # (half, pair process group)
         self.net_full = None         # [2 N h w, 8] fp32: both halves' network outputs after the pair exchange
         self._fwd_out = None
+        self.pair_peer = None        # peer-memory pair exchange (configure_split with a PeerWindow): dict of device arrays
 
-    def configure_split(self, half: int, pair_group):
+    def configure_split(self, half: int, pair_group, win=None, partner: Optional[int] = None, rows_pad: Optional[int] = None):
+        """win / partner: the rank's PeerWindow and the WINDOW rank of the other CFG half's owner of the same frames: the
+        pair exchange then is two kernels over NVLink (put my half into the partner's net_full + flag, wait for its half)
+        instead of an NCCL all-gather, and the whole step is graph-capturable."""
         self.split = (half, pair_group)
-        if self.net_full is None:
-            self.net_full = torch.empty(2 * self.N * self.h * self.w, 8, dtype=torch.float32, device=self.x.device)
+        rows = self.N * self.h * self.w
+        if win is None:
+            if self.net_full is None:
+                self.net_full = torch.empty(2 * rows, 8, dtype=torch.float32, device=self.x.device)
+            return
+        dev = self.x.device
+        # regions are sized by the LARGEST shard (rows_pad) so that every rank's window has the same layout
+        rp = rows if rows_pad is None else rows_pad
+        off = win.region(f"cfg.net_full.{rp}", 2 * rp * 8 * 4)
+        foff = win.region(f"cfg.flags.{rp}", 1024)      # +0: partner's half has landed; +256: partner has consumed mine
+        doff = win.region(f"cfg.ack_dummy.{rp}", 1024)
+        self.net_full = win.tensor(off, (2 * rows, 8), torch.float32)
+        half_bytes = rows * 8 * 4
+        z = lambda: torch.zeros(1, dtype=torch.int32, device=dev)
+        self.pair_peer = dict(
+            src=win.local(off + half * half_bytes), bytes=half_bytes,
+            dst=win.ptr_array([win.remote(partner, off + half * half_bytes)]), dst_flag=win.ptr_array([win.remote(partner, foff)]),
+            my_flag=win.ptr_array([win.local(foff)]),
+            ack_src=win.local(doff), ack_dst=win.ptr_array([win.remote(partner, doff + 512)]),
+            ack_flag_remote=win.ptr_array([win.remote(partner, foff + 256)]), ack_flag_mine=win.ptr_array([win.local(foff + 256)]),
+            c_put=z(), t_put=z(), c_wait=z(), c_ack_put=z(), t_ack=z(), c_ack_wait=z())
+        # prime the acknowledgement: every step WAITS for "the partner has consumed my previous half" before it stores, the
+        # first step has nothing to wait for
+        pp = self.pair_peer
+        ops.peer_put(pp["ack_src"], 16, 1, 16, pp["ack_dst"], 16, pp["ack_flag_remote"], 1, pp["c_ack_put"], pp["t_ack"], "cfg ack (prime)")
 
     def _prepare(self):
         ops.sampler_prepare(self.x, self.cond_frame, self.mask, self.concat_u, self.concat_c, self.sigmas, self.step,
@@ -64,17 +91,29 @@ class _LoopState:
         if self.split is None:
             return rt.forward(self.unet_in, self.c_noise, self.mask2, h, w)
         half, rows = self.split[0], N * h * w
+        out = self.net_full[half * rows:(half + 1) * rows] if self.pair_peer is not None else None   # straight into the exchange buffer
         return rt.forward(self.unet_in[half * rows:(half + 1) * rows], self.c_noise[half * N:(half + 1) * N],
-                          self.mask2[half * N:(half + 1) * N], h, w)
+                          self.mask2[half * N:(half + 1) * N], h, w, net_out=out)
 
     def _finish(self, net_out, num_steps: int):
-        if self.split is not None:                # guidance needs both halves of the frames this rank owns
+        if self.split is not None and self.pair_peer is not None:
+            # my half sits in net_full already (the output convolution wrote it there): store it into the partner's
+            # net_full once the partner has consumed the previous step's (ack), raise its flag, wait for its half
+            pp = self.pair_peer
+            ops.peer_wait(pp["ack_flag_mine"], 1, pp["c_ack_wait"], "cfg ack")
+            ops.peer_put(pp["src"], pp["bytes"], 1, pp["bytes"], pp["dst"], pp["bytes"], pp["dst_flag"], 1, pp["c_put"], pp["t_put"], "cfg half")
+            ops.peer_wait(pp["my_flag"], 1, pp["c_wait"], "cfg half")
+            net_out = self.net_full
+        elif self.split is not None:                # guidance needs both halves of the frames this rank owns
             import torch.distributed as dist
             full, pg = self.net_full, self.split[1]
             _lib.tape_host(lambda src=net_out: dist.all_gather_into_tensor(full, src, group=pg), "cfg pair all_gather")   # bind now: net_out is rebound below
             net_out = full
         ops.sampler_update(self.x, net_out, self.cond_frame, self.mask, self.scales, self.sigmas, self.step,
                            num_steps, self.N, self.h, self.w)
+        if self.split is not None and self.pair_peer is not None:      # the partner may overwrite my copy of its half now
+            pp = self.pair_peer
+            ops.peer_put(pp["ack_src"], 16, 1, 16, pp["ack_dst"], 16, pp["ack_flag_remote"], 1, pp["c_ack_put"], pp["t_ack"], "cfg ack")
 
     def one_step(self, rt, num_steps: int):
         self._prepare()
@@ -106,14 +145,15 @@ class _LoopState:
         if self.graph is None or self.graph_steps != num_steps:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
+            whole = self.split is None or self.pair_peer is not None      # no host-side collective in the step
             with torch.cuda.graph(g):             # capture does not execute
-                if self.split is None:
+                if whole:
                     self.one_step(rt, num_steps)
                 else:
                     self._prepare()
                     self._fwd_out = self._forward(rt)
             self.graph, self.graph_steps = g, num_steps
-        if self.split is None:
+        if self.split is None or self.pair_peer is not None:
             return self.graph.replay
 
         def run():
@@ -140,7 +180,7 @@ def fused_sample(sampler, den, x: torch.Tensor, cond: Dict, uc: Optional[Dict], 
     assert zc == 4 and N % T == 0
     rt = net._rt_get(net.diffusion_model, T, dev)
     if getattr(net, "frame_sharded", False):
-        return _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n, T)
+        return _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n, T, net)
     key = (N, h, w)
     states = rt.__dict__.setdefault("_loop_states", {})
     st: _LoopState = states.get(key)
@@ -184,7 +224,7 @@ def _run_steps(st: _LoopState, rt, n: int):
         step()
 
 
-def _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n: int, T: int) -> torch.Tensor:
+def _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n: int, T: int, net=None) -> torch.Tensor:
     """One clip spread over the ranks (vista_b200/sharded.py): the frames are sharded, and with an even world size
     the two CFG halves too.  Every rank receives the same full-clip inputs, advances the frames it owns and the
     final latent is all-gathered."""
@@ -198,9 +238,14 @@ def _fused_sample_sharded(sampler, rt, x, cond, uc, cond_frame, cond_mask, n: in
     states = rt.__dict__.setdefault("_loop_states", {})
     st = states.get((Tl, h, w))
     if st is None:
+        # NVLink peer window (collective on first use): the step's exchanges become kernels, the step a CUDA graph
+        win = net.peer_window(T, h, w, rt.cfg.model_channels, dev) if net is not None else None
+        if win is not None and hasattr(rt, "attach_window"):
+            rt.attach_window(win)
         st = states[(Tl, h, w)] = _LoopState(rt, Tl, h, w)
         if half is not None:
-            st.configure_split(half, rt.pair_group)
+            partner = (win.rank + win.world // 2) % win.world if win is not None else None
+            st.configure_split(half, rt.pair_group, win, partner, rows_pad=getattr(rt, "T_pad", Tl) * h * w)
     sigmas = sampler.discretization(n, device="cpu").to(torch.float32)
     x *= torch.sqrt(1.0 + sigmas[0] ** 2).to(dev)
     st.x.copy_(x[t0:t1])

@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvista_b200.so")
-SOURCES = ["host.cu", "gemm_tc.cu", "attn_tc.cu", "attn2_tc.cu", "attn5_tc.cu", "attn7_tc.cu", "misc.cu", "glue.cu", "mma_probe.cu"]
+SOURCES = ["host.cu", "gemm_tc.cu", "attn2_tc.cu", "attn7_tc.cu", "misc.cu", "glue.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -83,7 +83,7 @@ class GemmDesc(C.Structure):
         ("res1", C.c_void_p), ("ld_res1", C.c_int64), ("s_res1", C.c_float),
         ("res2", C.c_void_p), ("ld_res2", C.c_int64), ("s_res2", C.c_float),
         ("s_acc", C.c_float),
-        ("stats", C.c_void_p), ("stats_ld", C.c_int64), ("stats_col0", C.c_int32),
+        ("stats", C.c_void_p), ("stats_ld", C.c_int64), ("stats_col0", C.c_int32), ("h_pad", C.c_int32),
     ]
 
 
@@ -94,11 +94,7 @@ SIGNATURES = {
     "b200v_version": [],
     "b200v_device_info": [_P, _P, _P],
     "b200v_gemm": [C.POINTER(GemmDesc), _P],
-    "b200v_attention_spatial": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
-    "b200v_attention_spatial_v2": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v3": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
-    "b200v_attention_spatial_v4": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
-    "b200v_attention_spatial_v5": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_spatial_v7": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "b200v_attention_temporal": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_groupnorm_from_partials": [_P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P],
@@ -117,7 +113,6 @@ SIGNATURES = {
     "b200v_upsample2x": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_timestep_embedding": [_P, _I32, _I32, _F, _P, _I64, _P],
     "b200v_blend_emb": [_P, _P, _P, _P, _P, _P, _I32, _I32, _P],
-    "b200v_debug_mma_probe": [_I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P],
     "b200v_sampler_prepare": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I32, _I32, _I32, _P],
     "b200v_sampler_update": [_P, _P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "b200v_softmax_rows": [_P, _I64, _P, _I64, _I64, _I32, _P],
@@ -126,6 +121,14 @@ SIGNATURES = {
     "b200v_rollout_advance": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P],
     "b200v_ensemble_reward_scratch": [],
     "b200v_ensemble_reward": [_P, _I32, _I64, _P, _P, _P, _P],
+    "b200v_peer_alloc": [_I64, C.POINTER(C.c_void_p), _P],
+    "b200v_peer_open": [_P, C.POINTER(C.c_void_p)],
+    "b200v_peer_close": [_P],
+    "b200v_peer_free": [_P],
+    "b200v_peer_allreduce_max": [],
+    "b200v_peer_allreduce_f64": [_P, _I32, _P, _I64, _I64, _I32, _I32, _P, _P],
+    "b200v_peer_put": [_P, _I64, _I64, _I64, _P, _I64, _P, _I32, _P, _P, _P],
+    "b200v_peer_wait": [_P, _I32, _P, _P],
     "b200v_nchw_to_tokens": [_P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "b200v_tokens_to_nchw": [_P, _I32, _I64, _P, _I32, _I32, _I32, _I32, _P],
 }
@@ -165,7 +168,7 @@ def load() -> C.CDLL:
 # graph is not (the frame-sharded step with its NCCL calls); the same stability rules as for graph capture apply.
 # ---------------------------------------------------------------------------------------------------------------
 _tape: Optional[list] = None
-_NO_TAPE = {"b200v_ensemble_reward_scratch", "b200v_groupnorm_chunk", "b200v_groupnorm_chunk_for", "b200v_version", "b200v_device_info", "b200v_last_error"}
+_NO_TAPE = {"b200v_peer_alloc", "b200v_peer_open", "b200v_peer_close", "b200v_peer_free", "b200v_peer_allreduce_max", "b200v_ensemble_reward_scratch", "b200v_groupnorm_chunk", "b200v_groupnorm_chunk_for", "b200v_version", "b200v_device_info", "b200v_last_error"}
 
 
 class _Recorder:

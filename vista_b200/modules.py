@@ -123,6 +123,24 @@ class _RuntimeOwner:
             self._frame_world = world
         self._rt_invalidate()
 
+    def peer_window(self, T: int, h: int, w: int, model_channels: int, device):
+        """The NVLink peer window of this rank (vista_b200/peer.py), created on first use — collectively: every rank of the
+        group the clip is spread over calls this at the same point (the sharded sampler does).  None when the peer-memory
+        collectives are off (VISTA_B200_PEER=0) or the layout is not the one they serve (one clip per rank)."""
+        if not self.frame_sharded or os.environ.get("VISTA_B200_PEER", "1") == "0" or self.cfg_half is None \
+                or torch.device(device).type != "cuda":     # (the emulated-operator tests run the host logic on CPU tensors)
+            return None
+        if getattr(self, "_peer", None) is None:
+            from .peer import PeerWindow
+            fw = self._frame_world
+            tp = -(-T // fw)                                                # frames of the largest shard
+            ext = (tp + 2) * h * w * model_channels * 2                     # one halo-extended L0 activation
+            kv = fw * tp * h * w * 2 * model_channels * 2                   # gathered K|V of an L0 transformer
+            net = 2 * 2 * tp * h * w * 8 * 4                                # CFG pair exchange (double the rows for slack)
+            nbytes = (4 * ext + kv + net + (16 << 20)) if fw > 1 else (net + (4 << 20))
+            self._peer = PeerWindow(self.world_group, nbytes, device)
+        return self._peer
+
     def _rt_invalidate(self):
         self._runtime, self._runtime_key, self._cond_cache = None, None, None
 

@@ -143,13 +143,18 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
          res1: Optional[torch.Tensor] = None, s_res1: float = 1.0,
          res2: Optional[torch.Tensor] = None, s_res2: float = 1.0,
          s_acc: float = 1.0, act: int = 0, tile_n: Optional[int] = None, cin: Optional[int] = None,
-         stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+         stats: Optional[torch.Tensor] = None, h_pad: int = 0) -> torch.Tensor:
     """out = epilogue(tap-GEMM(a, w)).  ``a``: [tokens, >=cin] fp16 view; ``w``: [N, ntaps*cin] fp16;
     ``geom`` = (W, H, NB) turns on image taps (zero padded); act 2 = GEGLU (out has N/2 columns).
     ``stats`` = partials [tokens/128*4, N, 2] fp32 (may be a column slice of a wider matrix): the epilogue also writes the
     column sums / sums of squares of the output (GroupNorm statistics of the consumer without a pass over the tensor);
-    the token tiles are then the 128-consecutive-token ones of stats_box()."""
+    the token tiles are then the 128-consecutive-token ones of stats_box().
+    ``h_pad``: ``a`` holds h_pad extra rows of H before and after the H rows of ``geom`` (halo frames of the frame-sharded
+    (3,1,1) convolution): ``a`` is the extended [(NB (H + 2 h_pad) W), C] tensor, the output has NB H W rows."""
     tokens, lda = _rows(a)
+    if h_pad:
+        assert geom is not None and tokens == geom[2] * (geom[1] + 2 * h_pad) * geom[0]
+        tokens = geom[0] * geom[1] * geom[2]
     N, K = w.shape
     ntaps = len(taps)
     cin = cin if cin is not None else K // ntaps
@@ -185,6 +190,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
             and stats.stride(1) == 2 and stats.stride(0) % 2 == 0 and stats.shape[1] >= (N // 2 if act == 2 else N)
         assert stats.shape[0] >= -(-tokens // 128) * 4
         d.stats, d.stats_ld, d.stats_col0 = stats.data_ptr(), stats.stride(0) // 2, 0
+    d.h_pad = h_pad
     _count()
     n_out = N // 2 if act == 2 else N
     _prof_begin("gemm", f"M={tokens} N={N} K={K} taps={ntaps} act={act}", 2.0 * tokens * N * K,
@@ -198,14 +204,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
 
 # Spatial-attention kernel generation.  0 (default): by shape — v7 (persistent, two query tiles per CTA, P in tensor
 # memory, S / P / O in separate columns so that S(j+1) runs ahead of the softmax) for long sequences, v3 (one tile per CTA,
-# two CTAs per SM) for the short ones of the inner levels; 1 / 2 / 3 / 4 / 5 / 7 force one generation.
+# two CTAs per SM) for the short ones of the inner levels; 3 / 7 force one.  (Generations 1, 2, 4, 5, 6: measured, removed.)
 ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "0"))
+ATTN_LONG = int(os.environ.get("VISTA_B200_ATTN_LONG", "2048"))     # sequence length from which v7 runs
 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
     l = _lib.load()
-    fn = {1: l.b200v_attention_spatial, 2: l.b200v_attention_spatial_v2, 3: l.b200v_attention_spatial_v3,
-          4: l.b200v_attention_spatial_v4, 5: l.b200v_attention_spatial_v5, 7: l.b200v_attention_spatial_v7}[impl or ATTN_IMPL or (7 if seq >= 2048 else 3)]
+    fn = {3: l.b200v_attention_spatial_v3, 7: l.b200v_attention_spatial_v7}[impl or ATTN_IMPL or (7 if seq >= ATTN_LONG else 3)]
     _count(1)
     _prof_begin("attn_spatial", f"frames={frames} seq={seq} heads={heads}", 4.0 * 64 * heads * frames * seq * seq,
                 2.0 * 4 * frames * seq * heads * 64)
@@ -534,3 +540,33 @@ def ensemble_reward(members: Sequence[torch.Tensor]) -> torch.Tensor:
                "b200v_ensemble_reward")
     out._keepalive = (ptrs, tuple(members))      # the launch is asynchronous
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Peer-memory collectives (csrc/peer.cu): thin wrappers; the window bookkeeping lives in vista_b200/peer.py
+# ------------------------------------------------------------------------------------------------------------------
+def peer_allreduce_f64(data: torch.Tensor, windows_dev: torch.Tensor, slot_off: int, flag_off: int, rank: int, world: int,
+                       counter: torch.Tensor):
+    assert data.dtype == torch.float64 and data.is_contiguous()
+    _count(1)
+    _prof_begin("peer", f"allreduce_f64 n={data.numel()}", 0.0, 8.0 * data.numel() * world)
+    _lib.check(_lib.load().b200v_peer_allreduce_f64(data.data_ptr(), data.numel(), windows_dev.data_ptr(), slot_off, flag_off,
+                                                    rank, world, counter.data_ptr(), _stream()), "b200v_peer_allreduce_f64")
+    _prof_end()
+    return data
+
+
+def peer_put(src_ptr: int, src_pitch: int, rows: int, row_bytes: int, dsts_dev: torch.Tensor, dst_pitch: int,
+             flags_dev: torch.Tensor, n_dst: int, counter: torch.Tensor, ticket: torch.Tensor, detail: str = ""):
+    _count(1)
+    _prof_begin("peer", f"put {detail} bytes={rows * row_bytes} x{n_dst}", 0.0, float(rows * row_bytes * (n_dst + 1)))
+    _lib.check(_lib.load().b200v_peer_put(src_ptr, src_pitch, rows, row_bytes, dsts_dev.data_ptr(), dst_pitch, flags_dev.data_ptr(),
+                                          n_dst, counter.data_ptr(), ticket.data_ptr(), _stream()), "b200v_peer_put")
+    _prof_end()
+
+
+def peer_wait(flags_dev: torch.Tensor, n: int, counter: torch.Tensor, detail: str = ""):
+    _count(1)
+    _prof_begin("peer", f"wait {detail}", 0.0, 0.0)
+    _lib.check(_lib.load().b200v_peer_wait(flags_dev.data_ptr(), n, counter.data_ptr(), _stream()), "b200v_peer_wait")
+    _prof_end()

@@ -84,6 +84,67 @@ class ShardedUNetRuntime(UNetRuntime):
         self._tap_w: Dict[int, tuple] = {}
         self._frame_tables: Dict[tuple, torch.Tensor] = {}
         self.comm_bytes = 0
+        self.win = None               # PeerWindow (attach_window): the exchanges below become kernels over NVLink
+        self._ext: Dict[tuple, tuple] = {}
+        self._ext_of: Dict[int, tuple] = {}
+        self._peer_state: Dict[str, dict] = {}
+
+    # ------------------------------------------------------------------ NVLink peer-memory path
+    def attach_window(self, win):
+        """win: vista_b200.peer.PeerWindow over the group the clip is spread over.  With it (and one clip per rank, the
+        CFG-split layouts) the temporal couplings are stores into the neighbours' windows plus flags (csrc/peer.cu): no NCCL
+        call in the step, which then is a fixed launch sequence and replayed from a CUDA graph like the single-GPU one."""
+        self.win = win
+        self.has_collectives = False
+        # window ranks of the members of this runtime's frame group, in shard order
+        granks = list(range(self.world)) if self.group is None else dist.get_process_group_ranks(self.group)
+        wranks = list(range(win.world)) if win.group is None else dist.get_process_group_ranks(win.group)
+        self.wr = [wranks.index(g) for g in granks]          # shard index -> window rank
+        dev = self.dev
+        z = lambda: torch.zeros(1, dtype=torch.int32, device=dev)
+        W = self.world
+        # GroupNorm all-reduce: slots [2 parities][16][max doubles] + flags [2][16], in every window at the same offsets
+        amax = ops._lib.load().b200v_peer_allreduce_max()
+        self._ar = dict(slot=win.region("gn.ar.slots", 2 * 16 * amax * 8), flag=win.region("gn.ar.flags", 2 * 16 * 4), counter=z())
+        # the all-reduce kernel indexes windows by SHARD index: hand it this group's windows in shard order
+        self._ar["windows"] = win.ptr_array([win.bases[r] for r in self.wr])
+        # halo flags: +0 raised by the previous shard (its last frame has landed in my slot 0), +256 by the next shard
+        hf = win.region("halo.flags", 1024)
+        me = self.rank
+        st = dict(c_put_prev=z(), t_put_prev=z(), c_put_next=z(), t_put_next=z(), c_wait=z())
+        wait = []
+        if me > 0:
+            st["flag_on_prev"] = win.ptr_array([win.remote(self.wr[me - 1], hf + 256)])     # I am its next shard
+            wait.append(win.local(hf))
+        if me < W - 1:
+            st["flag_on_next"] = win.ptr_array([win.remote(self.wr[me + 1], hf)])
+            wait.append(win.local(hf + 256))
+        st["wait"] = win.ptr_array(wait) if wait else None
+        st["n_wait"] = len(wait)
+        self._halo = st
+        kf = win.region("kv.flags", 16 * 256)
+        peers = [r for r in range(W) if r != me]
+        self._kv = dict(flag_off=kf, peers=peers, c_put=z(), t_put=z(), c_wait=z(),
+                        flags_remote=win.ptr_array([win.remote(self.wr[r], kf + me * 256) for r in peers]),
+                        flags_local=win.ptr_array([win.local(kf + r * 256) for r in peers]))
+
+    def _peer_on(self, nb: int) -> bool:
+        return self.win is not None and nb == 1
+
+    def _ext_buffer(self, hw: int, Cc: int, which: int):
+        """Halo-extended activation of a temporal convolution in the window: frames [prev halo | T local | next halo] (+ unused
+        slots up to T_pad + 2 so that the layout is the same on every rank).  Zeroed at allocation: the clip ends keep their
+        zero halo = the convolution's zero padding (openaimodel.py:190-193)."""
+        key = (hw, Cc, which)
+        hit = self._ext.get(key)
+        if hit is None:
+            fb = hw * Cc * 2
+            off = self.win.region(f"ext.{hw}.{Cc}.{which}", (self.T_pad + 2) * fb)
+            ext = self.win.tensor(off, ((self.T + 2) * hw, Cc), torch.float16)
+            mid = ext[hw:(self.T + 1) * hw]
+            hit = self._ext[key] = (ext, mid, off, fb)
+            self._ext_of[mid.data_ptr()] = hit
+        return hit
 
     # ------------------------------------------------------------------ conditioning
     def set_conditioning(self, context: torch.Tensor, y: torch.Tensor):
@@ -112,16 +173,29 @@ class ShardedUNetRuntime(UNetRuntime):
 
     # ------------------------------------------------------------------ temporal GroupNorm
     def _fuse_stats(self, B, h, w) -> bool:
-        # the (3,1,1) convolutions get their halo corrections AFTER the main launch: statistics taken in its epilogue would
-        # miss them.  Frame-sharded steps keep the separate statistics pass.
+        # NCCL path: the (3,1,1) convolutions get their halo corrections AFTER the main launch, statistics taken in its epilogue
+        # would miss them -> separate statistics pass.  Peer path: the halos are in place before the ONE launch, the fused
+        # statistics are exact again.
+        if self._peer_on(B // self.T):
+            return super()._fuse_stats(B, h, w)
         return False
 
     def _gn_temporal(self, x, y, B, hw, norm, eps, silu, idx, fps, part=None):
         nb = B // fps
         Cc = norm[0].numel()
         sums = self.buf(f"gn.sums{nb}", nb * self.cfg.num_groups, 2, torch.float64)
-        ops.groupnorm_sums(x, B, hw, Cc, sums, fps, groups=self.cfg.num_groups, ws=self.gn_ws)
-        _lib.tape_host(lambda: dist.all_reduce(sums, group=self.group), "gn-sum all_reduce")
+        if part is not None:       # this rank's raw sums from the column partials its producing GEMM wrote
+            ops.groupnorm_from_partials(part, B, hw, Cc, eps, None, fps, self.cfg.num_groups, raw_sums=sums)
+        else:
+            ops.groupnorm_sums(x, B, hw, Cc, sums, fps, groups=self.cfg.num_groups, ws=self.gn_ws)
+        if self._peer_on(nb):
+            ar = self._ar
+            ops.peer_allreduce_f64(sums.view(-1), ar["windows"], ar["slot"], ar["flag"], self.rank, self.world, ar["counter"])
+            # the normalised activation goes straight into the halo-extended buffer of the (3,1,1) convolution that follows
+            which = 0 if y.data_ptr() == self.buf("rb.a1", y.shape[0], y.shape[1]).data_ptr() else 1
+            y = self._ext_buffer(hw, Cc, which)[1]
+        else:
+            _lib.tape_host(lambda: dist.all_reduce(sums, group=self.group), "gn-sum all_reduce")
         self.comm_bytes += sums.numel() * 8
         count = float(Cc // self.cfg.num_groups) * hw * self.T_full
         return ops.groupnorm_finalize_apply(x, y, B, hw, norm[0], norm[1], eps, silu, sums, count,
@@ -139,6 +213,23 @@ class ShardedUNetRuntime(UNetRuntime):
 
     def _tconv(self, a, lin: Lin, out, hw: int, nb: int, **epi):
         T, Cc = self.T, a.shape[1]
+        ext = self._ext_of.get(a.data_ptr()) if self._peer_on(nb) else None
+        if ext is not None:
+            # my boundary frames -> the neighbours' halo slots (NVLink stores + flag), wait for theirs, ONE convolution over
+            # the extended tensor (h_pad = 1): no correction GEMMs, fused statistics stay valid
+            ext_t, _, off, fb = ext
+            h, win, me = self._halo, self.win, self.rank
+            if me > 0:          # first frame -> slot T_prev + 1 of the previous shard's buffer
+                t_prev = self.shards[me - 1][1] - self.shards[me - 1][0]
+                dst = self._peer_ptrs(("hp", off, fb), lambda: [win.remote(self.wr[me - 1], off + (t_prev + 1) * fb)])
+                ops.peer_put(a.data_ptr(), fb, 1, fb, dst, fb, h["flag_on_prev"], 1, h["c_put_prev"], h["t_put_prev"], "halo->prev")
+            if me < self.world - 1:   # last frame -> slot 0 of the next shard's buffer
+                dst = self._peer_ptrs(("hn", off, fb), lambda: [win.remote(self.wr[me + 1], off)])
+                ops.peer_put(a.data_ptr() + (T - 1) * fb, fb, 1, fb, dst, fb, h["flag_on_next"], 1, h["c_put_next"], h["t_put_next"], "halo->next")
+            if h["n_wait"]:
+                ops.peer_wait(h["wait"], h["n_wait"], h["c_wait"], "halo")
+            self.comm_bytes += fb * ((me > 0) + (me < self.world - 1))
+            return self.gemm(ext_t, lin, out, taps=ops.TAPS_T3, geom=(hw, T, nb), h_pad=1, **epi)
         # boundary frames of the input go to the neighbours while the local convolution runs
         send_first = self.buf("halo.sf", nb * hw, Cc)
         send_last = self.buf("halo.sl", nb * hw, Cc)
@@ -165,6 +256,12 @@ class ShardedUNetRuntime(UNetRuntime):
                 o = ov[b, T - 1]
                 self.gemm(recv_next[b * hw:(b + 1) * hw], w2, o, s_acc=s_acc, res1=o)
         return out
+
+    def _peer_ptrs(self, key, make):
+        t = self._peer_state.get(key)
+        if t is None:
+            t = self._peer_state[key] = self.win.ptr_array(make())
+        return t
 
     # ------------------------------------------------------------------ temporal attention with gathered K|V
     def _frame_table(self, nb: int, hw: int) -> torch.Tensor:
@@ -198,13 +295,40 @@ class ShardedUNetRuntime(UNetRuntime):
             sub = (Lin(lin.w[:Cc], None, ops.pick_tile_n(Cc)), Lin(lin.w[Cc:], None, ops.pick_tile_n(2 * Cc)))
             self._tap_w[("qkv", lin.w.data_ptr())] = sub
         qkv = self.buf("tr.qkv", M, 3 * Cc)
-        send = self.buf("kv.send", nb * self.T_pad * hw, 2 * Cc)
+        send = self._kv_recv(nb, hw, Cc)[1] if self._peer_on(nb) else self.buf("kv.send", nb * self.T_pad * hw, 2 * Cc)
         self.gemm(n, sub[0], qkv[:, :Cc])
         self.gemm(n, sub[1], send[:M])
         return qkv
 
+    def _kv_recv(self, nb: int, hw: int, Cc: int):
+        """(gathered K|V [W * T_pad * hw, 2C] in the window, this rank's slab of it, slab bytes, region offset)."""
+        key = ("kv", hw, Cc)
+        hit = self._peer_state.get(key)
+        if hit is None:
+            slab = self.T_pad * hw * 2 * Cc * 2
+            # one region for every level: the first transformer met (highest resolution) has the largest K|V; region()
+            # refuses a later, larger request instead of overlapping a neighbour
+            off = self.win.region("kv.recv", self.world * slab)
+            recv = self.win.tensor(off, (self.world * self.T_pad * hw, 2 * Cc), torch.float16)
+            mine = recv[self.rank * self.T_pad * hw:(self.rank + 1) * self.T_pad * hw]
+            dsts = self.win.ptr_array([self.win.remote(self.wr[r], off + self.rank * slab) for r in self._kv["peers"]])
+            hit = self._peer_state[key] = (recv, mine, slab, off, dsts)
+        return hit
+
     def _attn_temporal(self, qkv, o, nb: int, hw: int, heads: int, Cc: int):
         T, Tp, W = self.T, self.T_pad, self.world
+        if self._peer_on(nb):
+            # all-gather by stores: my K|V slab (written by the projection GEMM into my own window) goes to the same slab of
+            # every peer's window, one flag per (peer, source); then wait for the W - 1 slabs addressed to me
+            recv, mine, slab, off, dsts = self._kv_recv(nb, hw, Cc)
+            kv = self._kv
+            nbytes = T * hw * 2 * Cc * 2
+            ops.peer_put(mine.data_ptr(), nbytes, 1, nbytes, dsts, nbytes, kv["flags_remote"], len(kv["peers"]), kv["c_put"], kv["t_put"],
+                         f"kv C={Cc} hw={hw}")
+            ops.peer_wait(kv["flags_local"], len(kv["peers"]), kv["c_wait"], "kv")
+            self.comm_bytes += nbytes * len(kv["peers"])
+            tab = self._frame_table(nb, hw)
+            return ops.attention_temporal_sharded(qkv[:, :Cc], recv[:, :Cc], recv[:, Cc:], o, nb, T, self.T_full, hw, heads, tab)
         send = self.buf("kv.send", nb * Tp * hw, 2 * Cc)
         recv = self.buf("kv.recv", W * nb * Tp * hw, 2 * Cc)
         if not self._kv_direct(nb):
