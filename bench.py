@@ -288,15 +288,29 @@ def run_ours(args):
     # ---- e2e: the public calls a user makes — engine.sample() (50 steps) -> engine.decode_first_stage() — with HOST
     #      (pinned) inputs and the decoded frames copied back to the host inside the timed region
     def e2e_once():
+        t_a = time.perf_counter()
         cc, ucc = to_dev(c_h), to_dev(uc_h)
         zz = z_h.to(dev, non_blocking=True)
         lat = eng.sample(cc, cond_frame=zz, uc=ucc, N=T, shape=(4, h, w), noise=noise_h)
+        torch.cuda.synchronize()
+        t_b = time.perf_counter()
         frames = eng.decode_first_stage(lat)
-        return frames.to("cpu", non_blocking=False)
+        torch.cuda.synchronize()
+        t_c = time.perf_counter()
+        out = frames.to("cpu", non_blocking=False)
+        return out, (t_b - t_a, t_c - t_b, time.perf_counter() - t_c)
+    # one untimed call first: the 50-step schedule gets its own captured step graph (num_steps is a kernel argument) and the
+    # allocator its blocks — one-off costs of the first call of a process, reported as `first_call_seconds`, not steady state
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = e2e_once()
+    e2e_once()
+    torch.cuda.synchronize()
+    e2e_first = time.perf_counter() - t0
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res, e2e_parts = e2e_once()
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
     n_e2e_steps = sampler.num_steps
@@ -344,8 +358,11 @@ def run_ours(args):
         "e2e": {"value": T / e2e_dt, "unit": "frames/s", "seconds": e2e_dt, "steps": n_e2e_steps,
                 "h2d_bytes_per_step": h2d / n_e2e_steps, "d2h_bytes_per_step": d2h / n_e2e_steps,
                 "h2d_bytes": h2d, "d2h_bytes": d2h,
+                "sample_seconds": e2e_parts[0], "decode_seconds": e2e_parts[1], "d2h_seconds": e2e_parts[2],
+                "first_call_seconds": e2e_first,
                 "scope": "engine.sample() (50 EDM steps, pinned host inputs) -> engine.decode_first_stage() -> 25 decoded "
-                         "fp32 frames copied to the host; wall clock around the public calls"},
+                         "fp32 frames copied to the host; wall clock around the public calls (second call of the process; "
+                         "the first one, which also captures the 50-step graph, is first_call_seconds)"},
     }
     if parity is not None or sharded:
         out["parity_rel_l2"] = parity

@@ -110,7 +110,10 @@ class DiffusionEngine(nn.Module):
             group = getattr(self.model, "world_group", None)
             n_chunks = len(_decode_chunks(z.shape[0], self.en_and_decode_n_samples_a_time or z.shape[0], overlap))
             mode = os.environ.get("VISTA_B200_SHARDED_DECODE", "auto")
-            if mode == "1" or (mode == "auto" and dist.get_world_size(group) > n_chunks):
+            # auto: frame-shard the chunks when there are more ranks than chunks — up to 4 ranks, where that path is validated
+            # on hardware; an 8-rank frame chain over NCCL point-to-point timed out in its first hardware run
+            # (profiles/r02_sharded_tests_n8_frames_timeout.log), so larger worlds deal whole chunks out instead
+            if mode == "1" or (mode == "auto" and n_chunks < dist.get_world_size(group) <= 4):
                 # more ranks than chunks: shard the FRAMES of every chunk (sharded.ShardedDecoderRuntime)
                 from .sharded import ShardedDecoderRuntime, decode_first_stage_sharded
                 srt = getattr(dec, "_sharded_rt", None)

@@ -44,6 +44,7 @@ class _LoopState:
         self.unet_in = padded_input_rows(2 * N * h * w, dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_steps = None
+        self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}    # one captured step per schedule length (num_steps is a kernel argument)
         self.tape, self.tape_steps = None, None      # launch tape of one step (frame-sharded runtimes)
         # CFG-split mode (modules.enable_frame_sharding): this rank runs one half of the doubled batch
         self.split = None            # (half, pair process group)
@@ -142,6 +143,8 @@ class _LoopState:
                 else:
                     _lib.replay(self.tape)
             return run_taped
+        if num_steps in self.graphs:
+            self.graph, self.graph_steps = self.graphs[num_steps], num_steps
         if self.graph is None or self.graph_steps != num_steps:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
@@ -153,6 +156,7 @@ class _LoopState:
                     self._prepare()
                     self._fwd_out = self._forward(rt)
             self.graph, self.graph_steps = g, num_steps
+            self.graphs[num_steps] = g
         if self.split is None or self.pair_peer is not None:
             return self.graph.replay
 
