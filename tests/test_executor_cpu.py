@@ -546,3 +546,71 @@ def test_cond_frames_embedder_on_emulated_ops_matches_reference(monkeypatch):
         assert emb(x) is x                         # latents pass through (encoders/modules.py:470-471)
     ref = torch.from_numpy(golden("cond_embedder_tiny")["out"])
     assert out.shape == ref.shape and rel_l2(out, ref) < 5e-3, rel_l2(out, ref)
+
+
+def _ensemble_worker(rank, world, port, q):
+    import os
+    import types
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from fake_ops import patched_ops as patched
+        from helpers import to_t as tt, unet_weights
+        from vista_b200 import fused as fused_mod
+        from vista_b200 import synth as sy
+        from vista_b200.diffusion import Denoiser, EulerEDMSampler
+        from vista_b200.modules import B200Wrapper, VideoUNet
+        from vista_b200.rollout import sample_ensemble
+        fused_mod.USE_GRAPH = False
+        cfg, sd = unet_weights("tiny")
+        unet = VideoUNet(in_channels=cfg.in_channels, model_channels=cfg.model_channels, out_channels=cfg.out_channels,
+                         num_res_blocks=cfg.num_res_blocks, attention_resolutions=list(cfg.attention_resolutions),
+                         channel_mult=list(cfg.channel_mult), num_head_channels=64, num_classes="sequential",
+                         context_dim=cfg.context_dim, adm_in_channels=cfg.adm_in_channels, extra_ff_mix_layer=True,
+                         use_spatial_context=True, merge_strategy="learned_with_images", video_kernel_size=[3, 1, 1],
+                         use_linear_in_transformer=True, action_control=True)
+        unet.load_state_dict(tt(sd), strict=True)
+        T, h, w, steps, K = 25, 8, 16, 2, 3
+        net = B200Wrapper(unet)
+        net._require_cuda = unet._require_cuda = lambda device: None
+        eng = types.SimpleNamespace(
+            model=net, denoiser=Denoiser({"target": "vista_b200.diffusion.VScalingWithEDMcNoise"}, num_frames=T), num_frames=T,
+            sampler=EulerEDMSampler(num_steps=steps, device="cpu", s_churn=0.0, s_tmin=0.0, s_tmax=999.0, s_noise=1.0, verbose=False,
+                                    discretization_config={"target": "vista_b200.diffusion.EDMDiscretization",
+                                                           "params": {"sigma_min": 0.002, "sigma_max": 700.0, "rho": 7.0}},
+                                    guider_config={"target": "vista_b200.diffusion.VanillaCFG", "params": {"scale": 2.5}}))
+        c, uc = sy.synth_conditioning(7, T, h, w, trajectory=True, context_dim=cfg.context_dim, adm=cfg.adm_in_channels)
+        _, z, _ = sy.synth_latents(7, T, h, w)
+        td = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+        noises = [torch.from_numpy(sy.normal(60 + i, "ens.noise", (T, 4, h, w), std=1.0)) for i in range(K)]
+        with patched(), torch.no_grad():
+            reward, members = sample_ensemble(eng, td(c), td(uc), torch.from_numpy(z), K, noises=noises, distributed=True)
+            reward1, members1 = (sample_ensemble(eng, td(c), td(uc), torch.from_numpy(z), K, noises=noises) if rank == 0 else (reward, members))
+        q.put((rank, float(reward), [m.numpy() for m in members], float(reward1), [m.numpy() for m in members1]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ensemble_members_dealt_over_two_ranks_on_emulated_ops():
+    """reward path (reward_utils.py:318-337) as replicas: member k sampled by rank k % 2 and broadcast; both ranks end with the
+    same members and reward, equal to the single-rank ensemble."""
+    import os
+    import numpy as np
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 36500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ensemble_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, r0, m0, r0s, m0s), (_, r1, m1, _, _) = res
+    assert r0 == r1 and all(np.array_equal(a, b) for a, b in zip(m0, m1))
+    assert r0 == r0s and all(np.array_equal(a, b) for a, b in zip(m0, m0s)), "distributed ensemble differs from the single-rank one"

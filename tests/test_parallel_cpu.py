@@ -18,40 +18,6 @@ def test_shard_arithmetic():
     assert [list(par.shard_units(5, 2, r)) for r in range(2)] == [[0, 1, 2], [3, 4]]
 
 
-def _worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        T = 25
-        full = torch.arange(T * 6, dtype=torch.float32).reshape(T, 2, 3)
-        a, b = par.frame_shards(T, world)[rank]
-        got = par.gather_frames(full[a:b].clone(), T)
-        ok_gather = torch.equal(got, full)
-        t = par.max_over_ranks(1.0 + rank)
-        stats = torch.tensor([[1.0 + rank, 2.0 * (rank + 1)]], dtype=torch.float64)
-        tot = par.reduce_group_stats(stats)
-        q.put((rank, ok_gather, t, tot.tolist()))
-    finally:
-        dist.destroy_process_group()
-
-
-def test_two_rank_gloo_collectives():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=120) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    for rank, ok_gather, t, tot in res:
-        assert ok_gather
-        assert t == 2.0                      # max over ranks
-        assert tot == [[3.0, 6.0]]           # 1+2, 2+4: identical on both ranks
-
-
 def _topology_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
