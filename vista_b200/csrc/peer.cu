@@ -20,7 +20,7 @@
 namespace vb {
 
 #ifndef VB_PEER_TIMEOUT_CYCLES
-#define VB_PEER_TIMEOUT_CYCLES (20000000000ll)   // ~10 s: a peer may still be compiling / capturing on the first step
+#define VB_PEER_TIMEOUT_CYCLES (120000000000ll)   // ~60 s: a peer may still be capturing its step graph (cudaFree storms with peer access on are slow); the NCCL watchdog of the caller is the outer bound
 #endif
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
