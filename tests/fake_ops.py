@@ -14,7 +14,33 @@ def _f(t):
 
 
 def gemm(a, w, out, *, taps=((0, 0),), geom=None, bias=None, rowvec=None, rv_div=1, rv_mod=1, res1=None, s_res1=1.0,
-         res2=None, s_res2=1.0, s_acc=1.0, act=0, tile_n=None, cin=None, stats=None):
+         res2=None, s_res2=1.0, s_acc=1.0, act=0, tile_n=None, cin=None, stats=None, h_pad=0):
+    if h_pad:
+        # `a` holds h_pad halo rows of H before and after the H output rows: fold them in as real neighbours, i.e. run the
+        # plain tap-GEMM over the extended image and keep the middle rows
+        W_, H_, NB_ = geom
+        He = H_ + 2 * h_pad
+        assert a.shape[0] == NB_ * He * W_
+        assert act == 0
+        tmp32 = torch.empty(NB_ * He * W_, out.shape[1], dtype=torch.float32)      # s_acc * (conv + bias), unrounded
+        gemm(a, w, tmp32, taps=taps, geom=(W_, He, NB_), bias=bias, s_acc=s_acc, act=0, tile_n=tile_n, cin=cin)
+        acc = tmp32.reshape(NB_, He, W_, -1)[:, h_pad:h_pad + H_].reshape(NB_ * H_ * W_, -1)
+        tokens = acc.shape[0]
+        if rowvec is not None:
+            rows = (torch.arange(tokens) // rv_div) % rv_mod
+            acc = acc + _f(rowvec)[rows][:, :acc.shape[1]]
+        assert act == 0
+        if res1 is not None:
+            acc = acc + s_res1 * _f(res1)
+        if res2 is not None:
+            acc = acc + s_res2 * _f(res2)
+        out.copy_(acc.to(out.dtype))
+        if stats is not None:
+            pad = (-tokens) % 128
+            v = F.pad(acc, (0, 0, 0, pad)).reshape(-1, 32, acc.shape[1])
+            stats[: v.shape[0], :acc.shape[1], 0] = v.sum(dim=1)
+            stats[: v.shape[0], :acc.shape[1], 1] = (v * v).sum(dim=1)
+        return out
     tokens = a.shape[0]
     N, K = w.shape
     ntaps = len(taps)
@@ -321,12 +347,14 @@ def sampler_update(x, net_out, cond_frame, mask, scales, sigmas, step_idx, num_s
     step_idx += 1
 
 
+from fake_peer import peer_allreduce_f64, peer_put, peer_wait      # noqa: E402  (emulated NVLink peer kernels)
+
 _PATCHED = ["gemm", "GNWorkspace", "groupnorm_scratch", "groupnorm", "conv3x3_small_cin", "im2col_s2_asym", "upsample2x",
             "softmax_rows", "nchw_to_tokens", "tokens_to_nchw", "time_mix_small", "groupnorm_sums",
             "groupnorm_finalize_apply", "groupnorm_from_partials", "groupnorm_apply", "layernorm", "attention_spatial", "attention_temporal",
             "attention_temporal_sharded", "timestep_embedding", "blend_emb", "im2col_s2", "sampler_prepare",
-            "sampler_update", "time_mix_small_u8", "rollout_advance", "ensemble_reward"]
-_NOT_TAPED = {"GNWorkspace", "groupnorm_scratch", "rollout_advance", "ensemble_reward"}
+            "sampler_update", "time_mix_small_u8", "rollout_advance", "ensemble_reward", "peer_put", "peer_wait", "peer_allreduce_f64"]
+_NOT_TAPED = {"GNWorkspace", "groupnorm_scratch", "rollout_advance", "ensemble_reward", "peer_put", "peer_wait", "peer_allreduce_f64"}
 
 
 @contextlib.contextmanager
