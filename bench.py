@@ -325,16 +325,19 @@ def run_ours(args):
         dt, e2e_dt, decode_s = float(tmax[0]), float(tmax[1]), float(tmax[2])
     step_s = dt / K
 
+    peer_on = getattr(st, "pair_peer", None) is not None or getattr(rt, "win", None) is not None
+    transport = ("stores into the peers' NVLink windows + flags (csrc/peer.cu), step replayed from a CUDA graph" if peer_on
+                 else "NCCL, step replayed from a launch tape")
     if world == 1:
         shard_desc = "single GPU"
     elif net.cfg_half is not None:
         shard_desc = (f"one clip over {world} GPUs: CFG halves x frames ({world // 2} frame shard(s) per half); per step a "
-                      f"pairwise all-gather of the 4-channel network output" +
+                      f"pairwise exchange of the 4-channel network output" +
                       ("" if world == 2 else ", and inside each half temporal K/V all-gather, GN-sum all-reduce, 1-frame halos") +
-                      " (NCCL); decode chunks dealt out over the ranks")
+                      f" [{transport}]; decode chunks dealt out over the ranks (frame-sharded up to 4 ranks)")
     else:
         shard_desc = (f"frames of one clip over {world} GPUs: temporal K/V all-gather, GN-sum all-reduce, 1-frame halos "
-                      f"(NCCL); decode chunks dealt out over the ranks")
+                      f"[{transport}]; decode chunks dealt out over the ranks")
     peaks = load_peaks()
     full = args.config == "full"
     ach = (F_STEP_TFLOP / step_s) if full else None        # whole-job TFLOP/s: all N GPUs work on the one clip

@@ -114,7 +114,7 @@ def _sharded_worker(rank, world, port, cfg_split, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,cfg_split", [(4, True), (8, True), (4, False)])
+@pytest.mark.parametrize("world,cfg_split", [(4, True), (8, True), (4, False), (8, False)])
 def test_sharded_sampler_on_emulated_ops(world, cfg_split):
     """One clip over 4 / 8 ranks (gloo, emulated operators): CFG halves x frame shards (sub-group collectives, pairwise
     exchange) and frames only, with the step recorded on the launch tape and replayed.  Every rank must end with the
@@ -340,7 +340,7 @@ def test_multi_round_rollout_through_the_reference_closure_on_emulated_ops(monke
 
 def test_engine_encode_sample_decode_on_emulated_ops(monkeypatch):
     """The DiffusionEngine surface end to end on emulated operators, built from configs/inference/vista_b200.yaml with
-    tiny sizes and the (experimental) B200 encoder plugged in: encode_first_stage(images) -> sample() ->
+    tiny sizes and the B200 encoder plugged in: encode_first_stage(images) -> sample() ->
     decode_first_stage(), each stage against the CPU oracle, plus the reference checkpoint key layout."""
     import os
     import yaml

@@ -1,7 +1,9 @@
 """``DiffusionEngine`` surface (vwm/models/diffusion.py:20-131,150-180,306-329) for the hot path: the attributes
 and methods ``sample_utils`` uses (.model, .denoiser, .first_stage_model, .scale_factor, .decode_first_stage,
-.sample, .ema_scope) on top of the B200 executors.  Training and the conditioner are out of scope and raise; the VAE encoder is the next row
-(§8f): ``encode_first_stage`` works when an (experimental) ``encoder_config: vista_b200.vae.Encoder`` is given, else raises."""
+.sample, .ema_scope) on top of the B200 executors, plus the SURVEY §8f rows as engine calls (``encode_first_stage`` with
+``encoder_config: vista_b200.vae.Encoder``, ``rollout``, ``sample_ensemble``, ``decode_first_stage_u8``).  Training is out of
+scope and raises; a conditioner is hosted when a ``conditioner_config`` is given (its ``cond_frames`` embedder can be
+``vista_b200.conditioner.VideoPredictionEmbedderWithEncoder``), not built otherwise."""
 from __future__ import annotations
 
 import contextlib
@@ -29,7 +31,7 @@ class FirstStage(nn.Module):
         if unknown:
             raise TypeError(f"vista_b200.engine.FirstStage: unexpected keyword(s) {unknown}")
         self.decoder = instantiate_from_config(decoder_config)
-        # optional: the experimental B200 encoder (vista_b200.vae.Encoder), keys
+        # optional: the B200 encoder (vista_b200.vae.Encoder), keys
         # ``first_stage_model.encoder.*`` as in the reference checkpoint
         if encoder_config is not None:
             self.encoder = instantiate_from_config(encoder_config)
@@ -138,7 +140,7 @@ class DiffusionEngine(nn.Module):
 
     @torch.no_grad()
     def encode_first_stage(self, x, noise: Optional[torch.Tensor] = None, sample: bool = True):
-        """diffusion.py:183-195.  Needs ``encoder_config`` (experimental B200 encoder).  The reference samples the
+        """diffusion.py:183-195.  Needs ``encoder_config`` (the B200 encoder).  The reference samples the
         posterior with device RNG (DiagonalGaussianRegularizer, sample=True): pass ``noise`` for a reproducible draw,
         ``sample=False`` for the mode."""
         enc = getattr(self.first_stage_model, "encoder", None)

@@ -14,7 +14,14 @@ The three temporal couplings of the UNet cross ranks:
     first frame  (linearity of the convolution), the halos travelling by point-to-point send/recv.
 
 Weights are replicated.  The sampler state is frame-local too; the latent is all-gathered once at the end.
-torch.distributed (NCCL) is the transport; the math stays in the C-ABI kernels.
+
+Two transports.  With an NVLink peer window attached (``attach_window``; the CFG-split layouts, one clip per rank) the three
+couplings are KERNELS over peer memory (csrc/peer.cu): the K|V projection writes its slab straight into the window and
+``peer_put`` stores it into every peer's window; the GroupNorm sums go through the rank-ordered ``peer_allreduce_f64`` (fused
+statistics stay on); the boundary frames are stored into the neighbours' halo slots of a halo-extended buffer and the
+convolution runs ONCE (tap-GEMM ``h_pad``).  No communicator call is left in the step, which is replayed from a CUDA graph.
+Otherwise (frames-only layouts, VISTA_B200_PEER=0) torch.distributed / NCCL carries them as described above and the step is
+replayed from a launch tape.  Either way the math stays in the C-ABI kernels.
 
 With an even number of ranks the classifier-free-guidance batch is split first (modules.enable_frame_sharding):
 ranks [0, W/2) run the unconditional clip, ranks [W/2, W) the conditional one, each half sharding the frames
@@ -357,11 +364,12 @@ def gather_latent(x_local: torch.Tensor, num_frames: int, group=None) -> torch.T
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# Frame-sharded VAE decode (EXPERIMENTAL, opt-in: VISTA_B200_SHARDED_DECODE=1).  The frames of every decode chunk are
-# spread over the ranks with the same three mechanisms as the UNet: the temporal GroupNorm's sums are all-reduced, the
-# (3,1,1) convolutions get one-frame halo corrections, and the closing 3-tap time mix (AE3DConv, temporal_ae.py:90-97)
-# reads one halo frame of its 3-channel input on each side.  Host-side orchestration only — no new kernel; validated on
-# emulated operators under gloo (tests/test_executor_cpu.py), not yet on hardware.
+# Frame-sharded VAE decode: the frames of every decode chunk are spread over the ranks with the NCCL mechanisms of the
+# UNet's round-1 path — the temporal GroupNorm's sums are all-reduced, the (3,1,1) convolutions get one-frame halo corrections,
+# the closing 3-tap time mix (AE3DConv, temporal_ae.py:90-97) reads one halo frame of its 3-channel input on each side.
+# Host-side orchestration only.  The engine picks it when there are more ranks than chunks, up to 4 ranks (validated on
+# hardware at 2 and 4: 1.5e-3 against the serial decode at 4, one more fp16 rounding per halo correction; 0.115 s per clip);
+# VISTA_B200_SHARDED_DECODE=1 forces it.
 # ---------------------------------------------------------------------------------------------------------------
 from .vae import DecoderRuntime, _decode_chunks      # noqa: E402  (kept next to its only user)
 

@@ -252,9 +252,9 @@ def decode_first_stage(rt: DecoderRuntime, z: torch.Tensor, scale_factor: float 
 
 # ---------------------------------------------------------------------------------------------------------------
 # VAE encoder (the next row).  Host executor over the validated kernels (tap-GEMM, GroupNorm,
-# GEMM-softmax-GEMM attention) plus one new gather (b200v_im2col_s2_asym).  EXPERIMENTAL: written against the pinned
-# oracle (tests/test_oracle_golden.py::test_encoder_matches_reference) but not yet run on hardware; its GPU test is
-# opt-in (VISTA_B200_TEST_ENCODER=1) until it has been.
+# GEMM-softmax-GEMM attention) plus one new gather (b200v_im2col_s2_asym).  Pinned by the oracle
+# (tests/test_oracle_golden.py::test_encoder_matches_reference) and, on hardware, by tests/test_decoder_gpu.py against the
+# real-reference fixtures (encode_first_stage rel-L2 ~1e-3).
 # ---------------------------------------------------------------------------------------------------------------
 class EncoderRuntime(DecoderRuntime):
     """``Encoder.forward`` (vwm/modules/diffusionmodules/model.py:527-557): conv_in, per level ResnetBlocks
@@ -382,7 +382,7 @@ def encode_first_stage(rt: EncoderRuntime, x: torch.Tensor, scale_factor: float 
 
 class Encoder(nn.Module):
     """``encoder_config.target`` stand-in for vwm.modules.diffusionmodules.model.Encoder: same keywords, same
-    ``state_dict`` keys, ``forward(x)`` -> (n, 2 z_channels, H/8, W/8) moments.  EXPERIMENTAL (see EncoderRuntime)."""
+    ``state_dict`` keys, ``forward(x)`` -> (n, 2 z_channels, H/8, W/8) moments."""
 
     def __init__(self, *, ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions=(), dropout=0.0, resamp_with_conv=True,
                  in_channels=3, resolution=256, z_channels=4, double_z=True, use_linear_attn=False, attn_type="vanilla",
@@ -546,7 +546,7 @@ def bench_decode(dcfg: DecoderConfig, rand_sd, dev, T: int, h: int, w: int, reps
     default process group (every rank must call; the caller takes the max over ranks)."""
     import os
     sd = rand_sd(decoder_param_specs(dcfg))
-    frame_sharded = parallel and os.environ.get("VISTA_B200_SHARDED_DECODE") == "1"     # experimental, opt-in
+    frame_sharded = parallel and os.environ.get("VISTA_B200_SHARDED_DECODE") == "1"     # force the frame-sharded decode
     if frame_sharded:
         from .sharded import ShardedDecoderRuntime, decode_first_stage_sharded
         rt = ShardedDecoderRuntime(dcfg, sd, dev)
