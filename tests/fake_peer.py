@@ -31,6 +31,7 @@ class FakePeerWindow:
         self.base = self.bases[self.rank]
         self.windows_dev = torch.tensor(self.bases, dtype=torch.int64)
         self._off, self._named = 0, {}
+        self._counters, self._done = {}, set()
         dist.barrier(group=group)
 
     def region(self, name, nbytes, align=1024):
@@ -60,6 +61,18 @@ class FakePeerWindow:
 
     def ptr_array(self, ptrs):
         return torch.tensor(ptrs, dtype=torch.int64)
+
+    def counter(self, name):
+        t = self._counters.get(name)
+        if t is None:
+            t = self._counters[name] = torch.zeros(1, dtype=torch.int32)
+        return t
+
+    def once(self, name):
+        if name in self._done:
+            return False
+        self._done.add(name)
+        return True
 
     def close(self):
         self._maps = []

@@ -70,18 +70,19 @@ class _LoopState:
         doff = win.region(f"cfg.ack_dummy.{rp}", 1024)
         self.net_full = win.tensor(off, (2 * rows, 8), torch.float32)
         half_bytes = rows * 8 * 4
-        z = lambda: torch.zeros(1, dtype=torch.int32, device=dev)
+        z = lambda name: win.counter(f"cfg.{rp}.{name}")     # counters live with the window (its flags outlive this state)
         self.pair_peer = dict(
             src=win.local(off + half * half_bytes), bytes=half_bytes,
             dst=win.ptr_array([win.remote(partner, off + half * half_bytes)]), dst_flag=win.ptr_array([win.remote(partner, foff)]),
             my_flag=win.ptr_array([win.local(foff)]),
             ack_src=win.local(doff), ack_dst=win.ptr_array([win.remote(partner, doff + 512)]),
             ack_flag_remote=win.ptr_array([win.remote(partner, foff + 256)]), ack_flag_mine=win.ptr_array([win.local(foff + 256)]),
-            c_put=z(), t_put=z(), c_wait=z(), c_ack_put=z(), t_ack=z(), c_ack_wait=z())
-        # prime the acknowledgement: every step WAITS for "the partner has consumed my previous half" before it stores, the
-        # first step has nothing to wait for
+            c_put=z("put"), t_put=z("ticket"), c_wait=z("wait"), c_ack_put=z("ack_put"), t_ack=z("ack_ticket"), c_ack_wait=z("ack_wait"))
+        # prime the acknowledgement once per window: every step WAITS for "the partner has consumed my previous half" before
+        # it stores, the very first step has nothing to wait for
         pp = self.pair_peer
-        ops.peer_put(pp["ack_src"], 16, 1, 16, pp["ack_dst"], 16, pp["ack_flag_remote"], 1, pp["c_ack_put"], pp["t_ack"], "cfg ack (prime)")
+        if win.once(f"cfg.{rp}.ack_primed"):
+            ops.peer_put(pp["ack_src"], 16, 1, 16, pp["ack_dst"], 16, pp["ack_flag_remote"], 1, pp["c_ack_put"], pp["t_ack"], "cfg ack (prime)")
 
     def _prepare(self):
         ops.sampler_prepare(self.x, self.cond_frame, self.mask, self.concat_u, self.concat_c, self.sigmas, self.step,

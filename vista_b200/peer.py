@@ -50,6 +50,8 @@ class PeerWindow:
         self.windows_dev = torch.tensor(self.bases, dtype=torch.int64, device=self.dev)
         self._off = 0
         self._named: Dict[str, Tuple[int, int]] = {}
+        self._counters: Dict[str, torch.Tensor] = {}
+        self._done = set()
         dist.barrier(group=group)          # every window exists and is zeroed before anyone stores into a peer
 
     # ------------------------------------------------------------------ layout
@@ -80,6 +82,22 @@ class PeerWindow:
 
     def ptr_array(self, ptrs: List[int]) -> torch.Tensor:
         return torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
+
+    def counter(self, name: str) -> torch.Tensor:
+        """Device-resident sequence counter (or ticket) of a channel, kept with the WINDOW: the flags it is compared with live
+        in the window too, so a runtime that is rebuilt (new weights, new loop state) must go on counting where the old one
+        stopped instead of restarting at zero against flags that already hold larger values."""
+        t = self._counters.get(name)
+        if t is None:
+            t = self._counters[name] = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        return t
+
+    def once(self, name: str) -> bool:
+        """True the first time it is asked for `name` (one-off protocol steps such as priming an acknowledgement flag)."""
+        if name in self._done:
+            return False
+        self._done.add(name)
+        return True
 
     def close(self):
         l = _lib.load()

@@ -107,18 +107,17 @@ class ShardedUNetRuntime(UNetRuntime):
         granks = list(range(self.world)) if self.group is None else dist.get_process_group_ranks(self.group)
         wranks = list(range(win.world)) if win.group is None else dist.get_process_group_ranks(win.group)
         self.wr = [wranks.index(g) for g in granks]          # shard index -> window rank
-        dev = self.dev
-        z = lambda: torch.zeros(1, dtype=torch.int32, device=dev)
         W = self.world
         # GroupNorm all-reduce: slots [2 parities][16][max doubles] + flags [2][16], in every window at the same offsets
         amax = ops._lib.load().b200v_peer_allreduce_max()
-        self._ar = dict(slot=win.region("gn.ar.slots", 2 * 16 * amax * 8), flag=win.region("gn.ar.flags", 2 * 16 * 4), counter=z())
+        self._ar = dict(slot=win.region("gn.ar.slots", 2 * 16 * amax * 8), flag=win.region("gn.ar.flags", 2 * 16 * 4), counter=win.counter("gn.ar"))
         # the all-reduce kernel indexes windows by SHARD index: hand it this group's windows in shard order
         self._ar["windows"] = win.ptr_array([win.bases[r] for r in self.wr])
         # halo flags: +0 raised by the previous shard (its last frame has landed in my slot 0), +256 by the next shard
         hf = win.region("halo.flags", 1024)
         me = self.rank
-        st = dict(c_put_prev=z(), t_put_prev=z(), c_put_next=z(), t_put_next=z(), c_wait=z())
+        st = dict(c_put_prev=win.counter("halo.put_prev"), t_put_prev=win.counter("halo.ticket_prev"),
+                  c_put_next=win.counter("halo.put_next"), t_put_next=win.counter("halo.ticket_next"), c_wait=win.counter("halo.wait"))
         wait = []
         if me > 0:
             st["flag_on_prev"] = win.ptr_array([win.remote(self.wr[me - 1], hf + 256)])     # I am its next shard
@@ -131,7 +130,7 @@ class ShardedUNetRuntime(UNetRuntime):
         self._halo = st
         kf = win.region("kv.flags", 16 * 256)
         peers = [r for r in range(W) if r != me]
-        self._kv = dict(flag_off=kf, peers=peers, c_put=z(), t_put=z(), c_wait=z(),
+        self._kv = dict(flag_off=kf, peers=peers, c_put=win.counter("kv.put"), t_put=win.counter("kv.ticket"), c_wait=win.counter("kv.wait"),
                         flags_remote=win.ptr_array([win.remote(self.wr[r], kf + me * 256) for r in peers]),
                         flags_local=win.ptr_array([win.local(kf + r * 256) for r in peers]))
 
