@@ -11,10 +11,12 @@ BASELINE.json; `value` is "denoised frames/sec at 25x576x1024, 50 EDM steps" =
 run (reported as `decode_ms`; null until the decoder lands, in which case `value` is sampler-only and
 `config.decode` says so).  Synthetic seeded weights / inputs (no checkpoint offline).
 
-N > 1 (torchrun): the ONE clip is spread over the ranks (vista_b200/sharded.py: CFG halves, then frames, with the
-temporal K/V all-gather, the GroupNorm-sum all-reduce and one-frame halos over NCCL) -> strong scaling: value =
-25 frames / max-over-ranks time of the same job.  In that mode the line also carries `parity_rel_l2`: the sharded
-K-step latent against the unsharded runtime on rank 0 (exit code 4 above 3e-3).
+N > 1 (torchrun): the ONE clip is spread over the ranks (vista_b200/sharded.py: CFG halves, then frames; the temporal K/V
+all-gather, the GroupNorm-sum all-reduce, the one-frame halos and the CFG pair exchange are kernels over NVLink peer windows
+— csrc/peer.cu — and the step a CUDA-graph replay; VISTA_B200_PEER=0 = the NCCL + launch-tape transport) -> strong scaling:
+value = 25 frames / max-over-ranks time of the same job.  In that mode the line also carries `parity_rel_l2`: the sharded
+K-step latent against the unsharded runtime on rank 0 (exit code 4 above 3e-3).  `e2e` is the second call of the public
+engine.sample() -> decode_first_stage() pair (the first, which captures the 50-step graph, is `first_call_seconds`).
 """
 from __future__ import annotations
 
