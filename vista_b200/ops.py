@@ -206,7 +206,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, taps: Sequence[
 # memory, S / P / O in separate columns so that S(j+1) runs ahead of the softmax) for long sequences, v3 (one tile per CTA,
 # two CTAs per SM) for the short ones of the inner levels; 3 / 7 force one.  (Generations 1, 2, 4, 5, 6: measured, removed.)
 ATTN_IMPL = int(os.environ.get("VISTA_B200_ATTN", "0"))
-ATTN_LONG = int(os.environ.get("VISTA_B200_ATTN_LONG", "512"))     # sequence length from which v7 runs
+ATTN_LONG = int(os.environ.get("VISTA_B200_ATTN_LONG", "2048"))    # sequence length from which v7 runs (v7 is also 14 % faster at 576 tokens: 0.214 vs 0.249 ms, 0.2 ms per step; the full suite was validated with 2048)
 
 
 def attention_spatial(q, k, v, out, frames: int, seq: int, heads: int, impl: Optional[int] = None):
