@@ -25,7 +25,7 @@ for r in rows[1:]:
 
 def family(name):
     if "tapgemm" in name: return "tapgemm (tcgen05)"
-    if "attn5" in name or "attn3" in name or "attn2" in name or "attn_spatial" in name: return "spatial attention (tcgen05)"
+    if "attn7" in name or "attn5" in name or "attn3" in name or "attn2" in name or "attn_spatial" in name: return "spatial attention (tcgen05)"
     if "attn_temporal" in name: return "temporal attention"
     if name.startswith("void vb::gn_") or "gn_" in name: return "groupnorm"
     if "layernorm" in name: return "layernorm"
