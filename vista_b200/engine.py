@@ -112,6 +112,12 @@ class DiffusionEngine(nn.Module):
             group = getattr(self.model, "world_group", None)
             n_chunks = len(_decode_chunks(z.shape[0], self.en_and_decode_n_samples_a_time or z.shape[0], overlap))
             mode = os.environ.get("VISTA_B200_SHARDED_DECODE", "auto")
+            if mode == "grouped":
+                # opt-in: chunks over sub-groups of <= 4 ranks that frame-shard them (8 ranks: 2 groups x 4 on the 2 chunks)
+                from .sharded import ShardedDecoderRuntime, decode_first_stage_grouped
+                cache = dec.__dict__.setdefault("_grouped_cache", {})
+                return decode_first_stage_grouped(dec.b200_config, lambda g: ShardedDecoderRuntime(dec.b200_config, dec.state_dict(), z.device, group=g),
+                                                  cache, z, self.scale_factor, self.en_and_decode_n_samples_a_time, overlap, world_group=group)
             # auto: frame-shard the chunks when there are more ranks than chunks — up to 4 ranks, where that path is validated
             # on hardware; an 8-rank frame chain over NCCL point-to-point timed out in its first hardware run
             # (profiles/r02_sharded_tests_n8_frames_timeout.log), so larger worlds deal whole chunks out instead
