@@ -1,6 +1,7 @@
-"""Sharded sampling (one clip over 2 GPUs, NCCL) must reproduce the single-GPU result and the REAL reference's
-golden sample, in both layouts: frames sharded (K/V all-gather, GN-sum all-reduce, halos) and CFG halves split
-(pairwise exchange of the network output, CUDA-graph replay of the local UNet).  Needs >= 2 CUDA devices (skipped otherwise).  Tolerance: the sharded path only
+"""Sharded sampling (one clip over 2 / 4 / 8 GPUs) must reproduce the single-GPU result and the REAL reference's
+golden sample, in both layouts: frames sharded over NCCL (K/V all-gather, GN-sum all-reduce, halos; launch tape) and CFG
+halves split — the NVLink peer-memory path (csrc/peer.cu: stores into the peers' windows + flags, whole step replayed from
+a CUDA graph), whose primitives are checked first (rank-ordered all-reduce, put / wait ring).  Needs >= 2 CUDA devices (skipped otherwise).  Tolerance: the sharded path only
 re-associates the temporal GroupNorm sums (rank partials), everything else is the same arithmetic; fp16
 rounding noise re-samples, so we require rel-L2 <= 3e-3 between the two and <= 5e-3 against the reference."""
 import os
