@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE — CPU restatement (fp32, plain torch functional ops) of the reference's
 iterative-denoising hot path.  It is the checker for the CUDA path; it is never shipped, never
 measured as the product and never used as a fallback.  Only ``tests/``,
-``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs import it.
+``__graft_entry__.smoke()`` and ``bench.py``'s baseline legs (cpu_baseline, ``--impl reference``, and the eager-GPU
+denominator ``gpu_eager_baseline``, where it runs on ``cuda`` as the stated port of the reference's eager path) import it.
 
 Pinned: ``tests/test_oracle_golden.py`` compares every function below with outputs of the real
 reference modules (generated in the build container by ``oracle/make_golden.py`` and committed
